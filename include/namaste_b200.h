@@ -1,0 +1,109 @@
+/* namaste_b200 -- C ABI of the B200-native Namaste single-transit likelihood path.
+ *
+ * Drop-in boundary for the MCMC likelihood hot path of hposborn/Namaste.  The
+ * reference has no native code; its "plugin API" for this path is three Python
+ * contracts.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference checkout):
+ *
+ *   nmb_lc_create*      <- the `lc[N,3]` argument of MonoOnlyLogProb (namaste/namaste.py:1345)
+ *                          plus the loop-invariant part of MonotransitModel.get_value
+ *                          (cadence = median(diff(t)), supersampling offsets; :1157-1159)
+ *   nmb_lnprob*         <- MonoOnlyLogProb(params, lc, priors, model)       (:1345-1349)
+ *                          = get_value (:1155-1164) -> occultquad
+ *                            (namaste/Crossfield_transit.py:690-970) -> likelihood (:1347)
+ *                            + MonoLnPrior (:1314-1332), for a whole ensemble [W,6]
+ *   nmb_model           <- MonotransitModel.get_value(t)                     (:1155-1164)
+ *   nmb_occultquad      <- Crossfield_transit.occultquad(z, p, gamma, retall=True) (:690)
+ *   nmb_lnprior         <- MonoLnPrior(params, priors)                       (:1314-1332)
+ *   nmb_sampler_*       <- emcee.EnsembleSampler(...).run_mcmc(...) as called at
+ *                          namaste/namaste.py:590-594 (stretch move, a = 2)
+ *
+ * Conventions: every function returns NMB_OK (0) or a negative code and records a
+ * thread-local message readable through nmb_last_error(); no C++ exception crosses
+ * the boundary.  Host buffers are owned by the caller and never written unless named
+ * `out`.  Device buffers behind the opaque handles are owned by the library.  A handle
+ * must not be used from two threads / two streams concurrently (it carries the
+ * reduction workspace).  `stream` is a cudaStream_t passed as void* (NULL = default).
+ * All floating-point data is IEEE binary64 ("double"), like the reference.
+ */
+#ifndef NAMASTE_B200_H
+#define NAMASTE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMB_OK 0
+#define NMB_ERR_ARG (-1)     /* bad argument (null pointer, size, dtype ...)             */
+#define NMB_ERR_CUDA (-2)    /* a CUDA runtime call failed; message has the detail       */
+#define NMB_ERR_PRECOND (-3) /* light curve violates the supersampling precondition      */
+#define NMB_ERR_NAN (-4)     /* NaN log-probability where emcee would raise ValueError   */
+
+/* evaluation strategy (results agree to rounding) */
+#define NMB_MODE_BRUTE 0    /* every fine sample of every timestamp is visited            */
+#define NMB_MODE_WINDOWED 1 /* exact: out-of-transit chi^2 from prefix sums, window only  */
+
+/* arithmetic type of the transit model */
+#define NMB_F64 64
+#define NMB_F32 32
+
+#define NMB_NPAR 6       /* tcen, b, vel, RpRs, LD1, LD2  (namaste.py:1153)                */
+#define NMB_PRIOR_COLS 6 /* lo, hi, kind(0 none,1 gaussian,2 normlim,3 evans), mu, sigma, pad */
+
+typedef struct nmb_lc nmb_lc;           /* one or more staged light curves, device resident */
+typedef struct nmb_sampler nmb_sampler; /* device-resident ensemble sampler state           */
+
+const char* nmb_last_error(void);
+const char* nmb_version(void);
+
+/* ---- light-curve staging ------------------------------------------------------------- */
+/* Stage one light curve (host pointers, n points each).  `oversamp` is the supersampling
+ * factor S (the reference hard-codes 10, namaste.py:1158).  Requires n >= 2, t finite and
+ * increasing with t[i+1] >= t[i] + cad*(S-1)/S (otherwise the reference's sort+resize
+ * binning mixes cadences; NMB_ERR_PRECOND). */
+int nmb_lc_create(const double* t, const double* flux, const double* err, int64_t n, int oversamp, nmb_lc** out);
+
+/* Stage `ncand` independent light curves.  Candidate c occupies t[c*stride .. c*stride+n[c]). */
+int nmb_lc_create_batch(const double* t, const double* flux, const double* err, const int64_t* n, int64_t ncand,
+                        int64_t stride, int oversamp, nmb_lc** out);
+void nmb_lc_destroy(nmb_lc* lc);
+int64_t nmb_lc_ncand(const nmb_lc* lc);
+int64_t nmb_lc_npoints(const nmb_lc* lc, int64_t cand);
+double nmb_lc_cadence(const nmb_lc* lc, int64_t cand);
+int nmb_lc_oversamp(const nmb_lc* lc);
+
+/* ---- ensemble log-probability ------------------------------------------------------------
+ * params  [ncand][W][6]   device, row = (tcen, b, vel, RpRs, LD1, LD2)
+ * priors  [ncand][6][6]   device prior table, may be NULL (=> no prior term, like an empty dict)
+ * lnprob  [ncand][W]      device out: loglike + lnprior
+ * loglike [ncand][W]      device out, may be NULL
+ * Asynchronous on `stream`. */
+int nmb_lnprob(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob, double* loglike,
+               int mode, int dtype, void* stream);
+
+/* Same with HOST buffers: copies params (and priors) to the device through pinned staging,
+ * launches, copies lnprob (and loglike if non-NULL) back and synchronises. */
+int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob, double* loglike,
+                    int mode, int dtype);
+
+/* model [W][n] device out for candidate `cand`: MonotransitModel.get_value for W parameter rows */
+int nmb_model(nmb_lc* lc, int64_t cand, const double* params, int64_t W, double* model, void* stream);
+
+/* out [4][n] device: F, lambda_e, lambda_d, eta_d for z[n] (device), like retall=True */
+int nmb_occultquad(const double* z, int64_t n, double rprs, double ld1, double ld2, double* out, void* stream);
+
+/* lnprior [W] device out; params [W][npar] device; priors [npar][6] device */
+int nmb_lnprior(const double* params, int64_t W, int npar, const double* priors, double* lnprior, void* stream);
+
+/* ---- measurement helpers (used by bench.py) ------------------------------------------------ */
+/* Sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), CUDA-event timed. */
+int nmb_measure_fp64_peak(double* tflops, double* ms);
+/* number of kernels this library has launched so far in this process */
+int64_t nmb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAMASTE_B200_H */

@@ -1,0 +1,375 @@
+// C-ABI entry points (include/namaste_b200.h): light-curve staging, launches, error plumbing.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/namaste_b200.h"
+#include "lnprob_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(NMB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+    } while (0)
+
+constexpr int kThreads = 128;  // sweep / window block size
+constexpr int kTPT = 4;        // timestamps per thread in the sweep -> 512-timestamp tiles
+constexpr int kTile = kThreads * kTPT;
+
+}  // namespace
+
+struct nmb_lc {
+    int64_t ncand = 0, nmax = 0, npad = 0;
+    int S = 0;
+    int device = 0;
+    std::vector<int64_t> n;
+    std::vector<double> cad;
+    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
+    long long* d_n = nullptr;
+    // reduction workspace (grown on demand)
+    double* d_partials = nullptr;
+    int* d_tickets = nullptr;
+    size_t partials_cap = 0, tickets_cap = 0;
+    // staging for the host-buffer entry point
+    double *h_pin = nullptr, *d_stage = nullptr;
+    size_t pin_cap = 0, stage_cap = 0;
+    cudaStream_t own_stream = nullptr;
+
+    nmb::LcView view() const {
+        nmb::LcView v;
+        v.t = d_t; v.f = d_f; v.w = d_w; v.pre_hi = d_pre_hi; v.pre_lo = d_pre_lo; v.off = d_off;
+        v.n = d_n; v.npad = npad; v.ncand = (int)ncand; v.S = S;
+        return v;
+    }
+};
+
+extern "C" const char* nmb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* nmb_version(void) { return "namaste_b200 0.1 (sm_100a)"; }
+extern "C" int64_t nmb_launch_count(void) { return g_launches.load(); }
+
+extern "C" void nmb_lc_destroy(nmb_lc* lc) {
+    if (!lc) return;
+    cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
+    cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
+    if (lc->h_pin) cudaFreeHost(lc->h_pin);
+    if (lc->own_stream) cudaStreamDestroy(lc->own_stream);
+    delete lc;
+}
+
+extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const double* err, const int64_t* n,
+                                   int64_t ncand, int64_t stride, int oversamp, nmb_lc** out) {
+    if (!t || !flux || !err || !n || !out) return fail(NMB_ERR_ARG, "nmb_lc_create: null pointer");
+    if (ncand < 1) return fail(NMB_ERR_ARG, "nmb_lc_create: ncand < 1");
+    if (oversamp < 1 || oversamp > nmb::kMaxS) return fail(NMB_ERR_ARG, "nmb_lc_create: oversamp must be in 1..32");
+    const int S = oversamp;
+    // np.arange(0, 1.0, 1/S) must have exactly S elements (namaste.py:1159)
+    if ((int64_t)std::ceil(1.0 / (1.0 / S)) != S)
+        return fail(NMB_ERR_ARG, "nmb_lc_create: arange(0,1,1/oversamp) does not have oversamp elements");
+    int64_t nmax = 0;
+    for (int64_t c = 0; c < ncand; ++c) {
+        if (n[c] < 2) return fail(NMB_ERR_ARG, "nmb_lc_create: each light curve needs >= 2 points");
+        if (n[c] > stride) return fail(NMB_ERR_ARG, "nmb_lc_create: n[c] > stride");
+        nmax = std::max(nmax, n[c]);
+    }
+    const int64_t npad = (nmax + kTile - 1) / kTile * kTile;
+    std::vector<double> ht(ncand * npad, 0.0), hf(ncand * npad, 1.0), hw(ncand * npad, 0.0);
+    std::vector<double> hph(ncand * (npad + 1), 0.0), hpl(ncand * (npad + 1), 0.0), hoff(ncand * S, 0.0);
+    std::vector<double> cads(ncand);
+    std::vector<double> d;
+    for (int64_t c = 0; c < ncand; ++c) {
+        const double* tc = t + c * stride;
+        const double* fc = flux + c * stride;
+        const double* ec = err + c * stride;
+        const int64_t nc = n[c];
+        d.resize(nc - 1);
+        for (int64_t i = 0; i < nc; ++i)
+            if (!std::isfinite(tc[i])) return fail(NMB_ERR_ARG, "nmb_lc_create: non-finite time stamp");
+        for (int64_t i = 0; i + 1 < nc; ++i) d[i] = tc[i + 1] - tc[i];
+        // np.median(np.diff(t)): mean of the two middle order statistics for an even count
+        const int64_t m = nc - 1;
+        std::nth_element(d.begin(), d.begin() + m / 2, d.end());
+        double cad = d[m / 2];
+        if (m % 2 == 0) {
+            const double lower = *std::max_element(d.begin(), d.begin() + m / 2);
+            cad = (lower + cad) / 2.0;
+        }
+        cads[c] = cad;
+        const double step = 1.0 / S;
+        for (int k = 0; k < S; ++k) hoff[c * S + k] = cad * (k * step);
+        // precondition for "sort + resize(N, S)" == per-timestamp bins
+        const double span = hoff[c * S + S - 1];
+        for (int64_t i = 0; i + 1 < nc; ++i) {
+            if (!(tc[i + 1] >= tc[i] + span)) {
+                char buf[200];
+                snprintf(buf, sizeof buf,
+                         "light curve %lld: t[%lld+1] - t[%lld] is smaller than cad*(S-1)/S; the reference's "
+                         "supersampling bins would mix cadences", (long long)c, (long long)i, (long long)i);
+                return fail(NMB_ERR_PRECOND, buf);
+            }
+        }
+        double ph = 0.0, pl = 0.0;  // double-double running sum of w*(f-1)^2
+        for (int64_t i = 0; i < nc; ++i) {
+            ht[c * npad + i] = tc[i];
+            hf[c * npad + i] = fc[i];
+            const double w = -2 * std::pow(ec[i], -2.0);  // -2*lc[:,2]**-2   (namaste.py:1347)
+            hw[c * npad + i] = w;
+            hph[c * (npad + 1) + i] = ph;
+            hpl[c * (npad + 1) + i] = pl;
+            const double r = fc[i] - 1.0;
+            const double term = w * (r * r);
+            const double s = ph + term;
+            const double bb = s - ph;
+            const double e = (ph - (s - bb)) + (term - bb);
+            pl += e;
+            ph = s;
+            // renormalise
+            const double s2 = ph + pl;
+            pl = pl - (s2 - ph);
+            ph = s2;
+        }
+        for (int64_t i = nc; i <= npad; ++i) {
+            hph[c * (npad + 1) + i] = ph;
+            hpl[c * (npad + 1) + i] = pl;
+        }
+        for (int64_t i = nc; i < npad; ++i) ht[c * npad + i] = tc[nc - 1];
+    }
+
+    nmb_lc* lc = new nmb_lc;
+    lc->ncand = ncand; lc->nmax = nmax; lc->npad = npad; lc->S = S;
+    lc->n.assign(n, n + ncand);
+    lc->cad = cads;
+    cudaGetDevice(&lc->device);
+    std::vector<long long> hn(n, n + ncand);
+    auto up = [&](double** dst, const std::vector<double>& src) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, src.size() * sizeof(double));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = cudaSuccess;
+    if ((e = up(&lc->d_t, ht)) != cudaSuccess || (e = up(&lc->d_f, hf)) != cudaSuccess ||
+        (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
+        (e = up(&lc->d_pre_lo, hpl)) != cudaSuccess || (e = up(&lc->d_off, hoff)) != cudaSuccess ||
+        (e = cudaMalloc(&lc->d_n, ncand * sizeof(long long))) != cudaSuccess ||
+        (e = cudaMemcpy(lc->d_n, hn.data(), ncand * sizeof(long long), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&lc->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        nmb_lc_destroy(lc);
+        return cuda_fail(e, "nmb_lc_create: staging");
+    }
+    *out = lc;
+    return NMB_OK;
+}
+
+extern "C" int nmb_lc_create(const double* t, const double* flux, const double* err, int64_t n, int oversamp,
+                             nmb_lc** out) {
+    return nmb_lc_create_batch(t, flux, err, &n, 1, n, oversamp, out);
+}
+
+extern "C" int64_t nmb_lc_ncand(const nmb_lc* lc) { return lc ? lc->ncand : 0; }
+extern "C" int64_t nmb_lc_npoints(const nmb_lc* lc, int64_t c) { return (lc && c >= 0 && c < lc->ncand) ? lc->n[c] : -1; }
+extern "C" double nmb_lc_cadence(const nmb_lc* lc, int64_t c) { return (lc && c >= 0 && c < lc->ncand) ? lc->cad[c] : NAN; }
+extern "C" int nmb_lc_oversamp(const nmb_lc* lc) { return lc ? lc->S : 0; }
+
+namespace {
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return NMB_OK;
+}
+
+template <int S>
+int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                 cudaStream_t st) {
+    const int ntiles = (int)(lc->npad / kTile);
+    // walkers per block: reuse of the staged tile vs. enough blocks to fill 148 SMs several times over
+    long long blocks1 = (long long)ntiles * W * lc->ncand;
+    int WT = (int)std::min<long long>(nmb::kWTMax, std::max<long long>(1, blocks1 / (148 * 8)));
+    const int groups = (W + WT - 1) / WT;
+    const size_t need_p = (size_t)lc->ncand * groups * WT * ntiles;
+    const size_t need_t = (size_t)lc->ncand * groups;
+    if (need_p > lc->partials_cap) {
+        cudaFree(lc->d_partials);
+        lc->d_partials = nullptr; lc->partials_cap = 0;
+        CU(cudaMalloc(&lc->d_partials, need_p * sizeof(double)));
+        lc->partials_cap = need_p;
+    }
+    if (need_t > lc->tickets_cap) {
+        cudaFree(lc->d_tickets);
+        lc->d_tickets = nullptr; lc->tickets_cap = 0;
+        CU(cudaMalloc(&lc->d_tickets, need_t * sizeof(int)));
+        CU(cudaMemset(lc->d_tickets, 0, need_t * sizeof(int)));
+        lc->tickets_cap = need_t;
+    }
+    auto kern = nmb::lnprob_sweep_kernel<S, kThreads, kTPT, false>;
+    const size_t smem = sizeof(nmb::SweepSmem<S, kThreads, kTPT>);
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid(ntiles, groups, (unsigned)lc->ncand);
+    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, WT, priors, lc->d_partials, lc->d_tickets, lnprob,
+                                       loglike, nullptr, 0);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
+}
+
+template <int S>
+int launch_window(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                  cudaStream_t st) {
+    auto kern = nmb::lnprob_window_kernel<S, kThreads>;
+    const size_t smem = sizeof(nmb::WindowSmem<S, kThreads>);
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid(W, (unsigned)lc->ncand);
+    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, priors, lnprob, loglike);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
+}
+
+template <int S>
+int launch_model(nmb_lc* lc, int cand, const double* params, int W, double* model, cudaStream_t st) {
+    const int ntiles = (int)((lc->n[cand] + kTile - 1) / kTile);
+    const int WT = 1;
+    auto kern = nmb::lnprob_sweep_kernel<S, kThreads, kTPT, true>;
+    const size_t smem = sizeof(nmb::SweepSmem<S, kThreads, kTPT>);
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid(ntiles, W, 1);
+    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, WT, nullptr, nullptr, nullptr,
+                                       nullptr, nullptr, model, cand);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
+}
+
+#define NMB_DISPATCH_S(S_, CALL)                  \
+    switch (S_) {                                 \
+        case 1: { constexpr int SS = 1; CALL; } break;   \
+        case 10: { constexpr int SS = 10; CALL; } break; \
+        case 11: { constexpr int SS = 11; CALL; } break; \
+        case 15: { constexpr int SS = 15; CALL; } break; \
+        default: { constexpr int SS = 0; CALL; } break;  \
+    }
+
+}  // namespace
+
+extern "C" int nmb_lnprob(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
+                          double* loglike, int mode, int dtype, void* stream) {
+    if (!lc || !params || !lnprob) return fail(NMB_ERR_ARG, "nmb_lnprob: null pointer");
+    if (W < 1 || W > (1 << 24)) return fail(NMB_ERR_ARG, "nmb_lnprob: W out of range");
+    if (dtype != NMB_F64) return fail(NMB_ERR_ARG, "nmb_lnprob: only NMB_F64 is implemented in this build");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = NMB_OK;
+    if (mode == NMB_MODE_BRUTE) {
+        NMB_DISPATCH_S(lc->S, rc = launch_sweep<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
+    } else if (mode == NMB_MODE_WINDOWED) {
+        NMB_DISPATCH_S(lc->S, rc = launch_window<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
+    } else {
+        return fail(NMB_ERR_ARG, "nmb_lnprob: unknown mode");
+    }
+    return rc;
+}
+
+extern "C" int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
+                               double* loglike, int mode, int dtype) {
+    if (!lc || !params || !lnprob) return fail(NMB_ERR_ARG, "nmb_lnprob_host: null pointer");
+    if (W < 1) return fail(NMB_ERR_ARG, "nmb_lnprob_host: W < 1");
+    const size_t C = (size_t)lc->ncand;
+    const size_t np = C * W * 6, npri = priors ? C * 36 : 0, nout = C * W * (loglike ? 2 : 1);
+    const size_t total = np + npri + nout;
+    if (total > lc->pin_cap) {
+        if (lc->h_pin) cudaFreeHost(lc->h_pin);
+        cudaFree(lc->d_stage);
+        lc->h_pin = nullptr; lc->d_stage = nullptr; lc->pin_cap = 0;
+        CU(cudaMallocHost(&lc->h_pin, total * sizeof(double)));
+        CU(cudaMalloc(&lc->d_stage, total * sizeof(double)));
+        lc->pin_cap = total;
+    }
+    cudaStream_t st = lc->own_stream;
+    std::memcpy(lc->h_pin, params, np * sizeof(double));
+    if (priors) std::memcpy(lc->h_pin + np, priors, npri * sizeof(double));
+    CU(cudaMemcpyAsync(lc->d_stage, lc->h_pin, (np + npri) * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* d_out = lc->d_stage + np + npri;
+    int rc = nmb_lnprob(lc, lc->d_stage, W, priors ? lc->d_stage + np : nullptr, d_out,
+                        loglike ? d_out + C * W : nullptr, mode, dtype, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(lc->h_pin + np + npri, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::memcpy(lnprob, lc->h_pin + np + npri, C * W * sizeof(double));
+    if (loglike) std::memcpy(loglike, lc->h_pin + np + npri + C * W, C * W * sizeof(double));
+    return NMB_OK;
+}
+
+extern "C" int nmb_model(nmb_lc* lc, int64_t cand, const double* params, int64_t W, double* model, void* stream) {
+    if (!lc || !params || !model) return fail(NMB_ERR_ARG, "nmb_model: null pointer");
+    if (cand < 0 || cand >= lc->ncand) return fail(NMB_ERR_ARG, "nmb_model: candidate index out of range");
+    if (W < 1 || W > 65535) return fail(NMB_ERR_ARG, "nmb_model: W must be in 1..65535");
+    int rc = NMB_OK;
+    NMB_DISPATCH_S(lc->S, rc = launch_model<SS>(lc, (int)cand, params, (int)W, model, (cudaStream_t)stream));
+    return rc;
+}
+
+extern "C" int nmb_occultquad(const double* z, int64_t n, double rprs, double ld1, double ld2, double* out,
+                              void* stream) {
+    if (!z || !out) return fail(NMB_ERR_ARG, "nmb_occultquad: null pointer");
+    if (n < 0) return fail(NMB_ERR_ARG, "nmb_occultquad: n < 0");
+    if (n == 0) return NMB_OK;
+    const int threads = 128;
+    const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
+    nmb::occultquad_array_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(z, n, rprs, ld1, ld2, out);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
+}
+
+extern "C" int nmb_lnprior(const double* params, int64_t W, int npar, const double* priors, double* lnprior,
+                           void* stream) {
+    if (!params || !priors || !lnprior) return fail(NMB_ERR_ARG, "nmb_lnprior: null pointer");
+    if (W < 1 || npar < 1) return fail(NMB_ERR_ARG, "nmb_lnprior: bad sizes");
+    nmb::lnprior_kernel<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(params, W, npar, priors, lnprior);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
+}
+
+extern "C" int nmb_measure_fp64_peak(double* tflops, double* ms_out) {
+    if (!tflops) return fail(NMB_ERR_ARG, "nmb_measure_fp64_peak: null pointer");
+    double* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = 148 * 8, threads = 256;
+    for (int rep = 0; rep < 2; ++rep) nmb::dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        nmb::dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    g_launches += 7;
+    const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return NMB_OK;
+}

@@ -1,0 +1,150 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against fixtures produced by the
+reference's own code (tests/golden, see oracle/gen_golden.py) and against the oracle.
+
+Tolerances: BASELINE.json north_star asks for 1e-10 relative on lnprob in FP64; the
+element-level checks are much tighter because the kernels keep the reference's operation
+order (differences come only from libm and from per-element Bulirsch convergence)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, priors_from_table
+
+pytestmark = pytest.mark.gpu
+
+LNPROB_RTOL = 1e-10   # north-star tolerance
+LNPROB_RTOL_TIGHT = 2e-13  # what the implementation actually achieves (regression guard)
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import namaste_b200
+    return namaste_b200
+
+
+def rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def test_occultquad_all_cases(nb):
+    g = load_golden("occultquad_cases")
+    z, p, g1, g2 = g["z"], g["p"], g["g1"], g["g2"]
+    key = np.column_stack((p, g1, g2))
+    worst = 0.0
+    start = 0
+    while start < len(z):
+        stop = start
+        while stop < len(z) and np.array_equal(key[stop], key[start]):
+            stop += 1
+        out = np.column_stack(nb.occultquad(z[start:stop], p[start], (g1[start], g2[start]), retall=True))
+        ref_each = g["each"][start:stop]
+        ref_batch = g["batch"][start:stop]
+        nan_ref = np.isnan(ref_each)
+        assert np.array_equal(np.isnan(out), nan_ref)
+        ok = ~nan_ref
+        d = np.abs(out[ok] - ref_each[ok])
+        worst = max(worst, d.max())
+        # per-element reference values: libm-level agreement
+        assert d.max() < 5e-14, (p[start], g1[start], g2[start], d.max())
+        # batch-coupled reference values (what the reference returns for the whole array)
+        okb = ~np.isnan(ref_batch)
+        assert np.abs(out[okb] - ref_batch[okb]).max() < 5e-14
+        start = stop
+    print("occultquad worst abs deviation:", worst)
+
+
+@pytest.mark.parametrize("mode", ["brute", "windowed"])
+def test_logged_known_answers(nb, mode):
+    g = load_golden("kat_epic203311200")
+    pri = priors_from_table(g["priors"])
+    model = nb.MonotransitModel(*g["params"][0])
+    for th, nll, ll, lp in zip(g["params"], g["nll_logged"], g["ll"], g["lp"]):
+        got = nb.MonoOnlyNegLogProb(th, g["lc"], pri, model, mode=mode)
+        assert abs(got - nll) / nll < 5e-11          # vs the value the reference logged in 2018
+        assert abs(got + (ll + lp)) / nll < LNPROB_RTOL_TIGHT  # vs the reference run here on the same lc
+    assert np.array_equal(model.get_parameter_vector(), g["params"][-1])
+
+
+@pytest.mark.parametrize("name", ["config1_epic203311200", "synth_k2_s11", "synth_kepler_s15",
+                                  "synth_tess_s10", "synth_tess_s1"])
+@pytest.mark.parametrize("mode", ["brute", "windowed"])
+def test_lnprob_fixtures(nb, name, mode):
+    g = load_golden(name)
+    S = int(g["oversamp"]) if "oversamp" in g.files else 10
+    lc = nb.LightCurve(g["lc"], oversamp=S)
+    lnp, ll = lc.lnprob(g["walkers"], g["priors"], mode=mode, return_loglike=True)
+    ref_ll, ref_lp = g["ll"], g["lp"]
+    finite = np.isfinite(ref_ll + ref_lp)
+    assert np.array_equal(np.isfinite(lnp), finite)
+    r_ll = rel(ll[finite], ref_ll[finite]).max()
+    r_lnp = rel(lnp[finite], (ref_ll + ref_lp)[finite]).max()
+    print(name, mode, "max rel ll", r_ll, "lnprob", r_lnp)
+    assert r_ll < LNPROB_RTOL and r_lnp < LNPROB_RTOL
+    assert r_ll < LNPROB_RTOL_TIGHT and r_lnp < LNPROB_RTOL_TIGHT
+    lc.close()
+
+
+def test_model_values(nb):
+    g = load_golden("kat_epic203311200")
+    lc = nb.LightCurve(g["lc"], oversamp=10)
+    m = lc.model(g["params"])
+    assert np.abs(m - g["model"]).max() < 4e-16
+    for name in ["synth_k2_s11", "synth_kepler_s15", "synth_tess_s1"]:
+        s = load_golden(name)
+        lcs = nb.LightCurve(s["lc"], oversamp=int(s["oversamp"]))
+        m = lcs.model(s["walkers"][:4])
+        assert np.abs(m - s["model4"]).max() < 4e-16, name
+    mm = nb.MonotransitModel(*g["params"][0])
+    assert np.abs(mm.get_value(g["lc"][:, 0]) - g["model"][0]).max() < 4e-16
+
+
+def test_lnprior(nb):
+    g = load_golden("synth_k2_s11")
+    pri = priors_from_table(g["priors"])
+    got = nb.MonoLnPrior(g["walkers"], pri)
+    assert rel(got, g["lp"]).max() < 1e-13
+    assert abs(nb.MonoLnPrior(g["walkers"][0], pri) - g["lp"][0]) <= 1e-13 * abs(g["lp"][0])
+    assert nb.MonoLnPrior(g["walkers"][0], {}) == 0.0
+
+
+def test_brute_vs_windowed_vs_oracle_random_box(nb):
+    """Seeded random parameter boxes on a small synthetic light curve, checked against the
+    oracle evaluated on the same inputs (sizes the oracle finishes in seconds)."""
+    from oracle import namaste_oracle as o
+    rng = np.random.default_rng(5)
+    n, cad = 700, 0.0204318
+    t = 2000.0 + cad * np.arange(n)
+    t = t[(np.arange(n) % 97) != 13]            # a few single-cadence gaps
+    theta = np.array([t[len(t) // 2] + 0.3 * cad, 0.3, 4.0, 0.08, 0.4, 0.25])
+    flux = o.get_value(theta, t) + 1e-4 * rng.standard_normal(len(t))
+    lc = np.column_stack((t, flux, np.full(len(t), 1e-4)))
+    W = 64
+    pos = np.column_stack([rng.uniform(t[0] - 0.5, t[-1] + 0.5, W), rng.uniform(-0.2, 1.4, W),
+                           rng.uniform(0.0, 8.0, W), rng.uniform(-0.1, 0.7, W),
+                           rng.uniform(-0.2, 1.2, W), rng.uniform(-0.3, 1.0, W)])
+    g = load_golden("kat_epic203311200")
+    tab = g["priors"].copy()
+    tab[0, :2] = [theta[0] - 0.2, theta[0] + 0.2]
+    pri = priors_from_table(tab)
+    ref = o.lnprob_ensemble(pos, lc, pri)
+    staged = nb.LightCurve(lc, oversamp=10)
+    for mode in ("brute", "windowed"):
+        got = staged.lnprob(pos, pri, mode=mode)
+        assert rel(got, ref).max() < LNPROB_RTOL_TIGHT, mode
+    assert np.allclose(nb.MonoOnlyLogProb(pos, lc, pri), ref, rtol=LNPROB_RTOL_TIGHT, atol=0)
+
+
+def test_errors_are_loud(nb):
+    g = load_golden("kat_epic203311200")
+    lc = g["lc"].copy()
+    lc[5, 0] = lc[4, 0] + 1e-6  # violates the supersampling precondition
+    with pytest.raises(ValueError):
+        nb.LightCurve(lc)
+    with pytest.raises(ValueError):
+        nb.LightCurve(g["lc"][:1])
+    with pytest.raises(ValueError):
+        nb.LightCurve(g["lc"], oversamp=0)
+    nan_par = g["params"][0].copy()
+    nan_par[4] = np.nan
+    assert np.isnan(nb.MonoOnlyLogProb(nan_par, g["lc"], priors_from_table(g["priors"])))
