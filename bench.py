@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the Namaste likelihood hot path on B200 (driver contract: one JSON line).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload k2|kepler|epic]
+
+Metric (BASELINE.json): walker x timestamp log-probability evaluations per second.
+One *step* = one full-ensemble lnprob evaluation (W walkers x N timestamps x S supersamples,
+likelihood + priors) on synthetic input of BASELINE config 2 ("synthetic K2 long-cadence
+light curve, 4k points, supersampling x11, 1024 walkers").  With N > 1 GPUs every rank runs
+an independent candidate of that shape (the reference's batch-of-candidates mode: no data-path
+collective), so per-GPU work is fixed ("weak" scaling) and `value` is the sum over ranks.
+
+`value`   : brute-force kernel (every supersample of every timestamp is visited and classified),
+            inputs resident in HBM, CUDA-event timed per step with an L2 flush between steps.
+`e2e`     : the same evaluation through the public host API (numpy params in, numpy lnprob out):
+            pinned H2D of the walker positions and D2H of the log-probabilities every step.
+`windowed`: the exact prefix-sum/window kernel (product default), reported separately and never
+            as a roofline fraction.
+`roofline`: FP64-pipe bound; algorithmic FLOPs per SURVEY.md 8(d) convention / event time,
+            against a DFMA microbenchmark measured in the same process.
+`cpu_baseline`: the NumPy oracle (port of the reference's CPU path) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (cfg id, N, cadence, t0, sigma, S, W)
+    "k2": (2, 4000, 0.0204318, 2061.0, 5.4e-5, 11, 1024),
+    "kepler": (3, 65000, 0.02043361, 131.5, 1e-4, 15, 4096),
+    "epic": (1, 2828, 0.0204318, 2061.0, 5.4e-5, 10, 100),
+    "tess": (5, 500000, 2.0 / 1440, 1325.0, 6e-4, 10, 2048),
+}
+WORKLOAD_DESC = {
+    "k2": "BASELINE configs[1]: synthetic K2 long-cadence, N=4000, S=11, W=1024",
+    "kepler": "BASELINE configs[2]: synthetic Kepler long-cadence, N=65000, S=15, W=4096",
+    "epic": "BASELINE configs[0] shape: N=2828, S=10, W=100 (synthetic noise)",
+    "tess": "BASELINE configs[4] per-GPU share: synthetic TESS 2-min, N=500000, S=10, W=2048",
+}
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic workload (SURVEY.md 8d recipe).  The noiseless model is drawn with plain NumPy
+# geometry + the GPU model itself is NOT used here; the oracle is only needed for cpu_baseline.
+def make_workload(name, seed_offset=0):
+    cfg, n, cad, t0, sigma, S, W = WORKLOADS[name]
+    rng = np.random.default_rng(151203722 + cfg + 1000 * seed_offset)
+    t = t0 + cad * np.arange(n)
+    theta = np.array([t[n // 2] + 0.37 * cad, 0.5, 3.0, 0.06, 0.34, 0.30])
+    # box-shaped stand-in for the transit (depth p^2) + white noise: timing does not depend on the
+    # exact injected shape, and this keeps bench.py independent of oracle/ for the GPU arm
+    z = np.sqrt(theta[1] ** 2 + (theta[2] * (t + 0.45 * cad - theta[0])) ** 2)
+    flux = 1.0 - theta[3] ** 2 * (z < 1.0) + sigma * rng.standard_normal(n)
+    lc = np.column_stack((t, flux, np.full(n, sigma)))
+    tdur = 2 * (1 + theta[3]) * np.sqrt(1 - (theta[1] / (1 + theta[3])) ** 2) / theta[2]
+    ptab = np.array([
+        [theta[0] - 0.3 * tdur, theta[0] + 0.3 * tdur, 0, 0, 0, 0],
+        [0.0, 1.25, 0, 0, 0, 0],
+        [0, theta[2] * 1.6, 2, theta[2] * 1.1, theta[2] * 0.12, 0],
+        [0.02, 0.25, 0, 0, 0, 0],
+        [0, 1.0, 1, theta[4], 0.038, 0],
+        [0, 1.0, 1, theta[5], 0.022, 0],
+    ])
+    # initial ensemble: 95% tight ball around the truth, 5% uniform in the prior box
+    pos = theta[None, :] * (1 + 1e-3 * rng.standard_normal((W, 6)))
+    nbox = max(1, W // 20)
+    pos[:nbox] = ptab[:, 0] + (ptab[:, 1] - ptab[:, 0]) * rng.uniform(0, 1, (nbox, 6))
+    return dict(name=name, lc=lc, theta=theta, priors=ptab, pos=pos, S=S, W=W, N=n, cad=cad)
+
+
+def count_samples(wl):
+    """Per-ensemble counts of fine samples: total, interior (planet inside the disc) and
+    ingress/egress, for the FLOP formula of SURVEY.md 8(d)."""
+    t, S, cad = wl["lc"][:, 0], wl["S"], wl["cad"]
+    off = cad * np.arange(0, 1.0, 1 / S)
+    m_int = m_edge = 0
+    for par in wl["pos"]:
+        tcen, b, vel, rp = par[0], par[1], par[2], abs(par[3])
+        h2 = (1 + rp) ** 2 - b * b
+        if h2 <= 0:
+            continue
+        if vel == 0:
+            sel = np.arange(len(t))
+        else:
+            half = np.sqrt(h2) / abs(vel) + 2 * cad
+            sel = np.where(np.abs(t - tcen) < half)[0]
+        if len(sel) == 0:
+            continue
+        ft = (t[sel, None] + off[None, :]).ravel()
+        z = np.sqrt(b * b + (vel * (ft - tcen)) ** 2)
+        inner = z < abs(1 - rp)
+        m_int += int(np.sum(inner))
+        m_edge += int(np.sum((z < 1 + rp) & ~inner))
+    return wl["W"] * wl["N"] * S, m_int, m_edge
+
+
+def algorithmic_flops(wl):
+    m, m_int, m_edge = count_samples(wl)
+    return m * 7 + m_int * 143 + m_edge * 180 + wl["W"] * wl["N"] * 5 + wl["W"] * 40, (m, m_int, m_edge)
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t_begin or ts > t_end + 0.2:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+def _oracle_walker(args):
+    from oracle import namaste_oracle as o
+    par, lc, pri, S = args
+    return o.mono_only_logprob(par, lc, pri, S)
+
+
+def _priors_dict(tab):
+    names = ["mean:tcen", "mean:b", "mean:vel", "mean:RpRs", "mean:LD1", "mean:LD2"]
+    kinds = {1: "gaussian", 2: "normlim", 3: "evans"}
+    return {nm: ([r[0], r[1]] if int(r[2]) == 0 else [r[0], r[1], kinds[int(r[2])], r[3], r[4]])
+            for nm, r in zip(names, tab)}
+
+
+def cpu_reference_rate(wl, budget_s, pool, cores, nwalk=None):
+    """wt/s of the NumPy oracle (the reference's CPU path restated) on `cores` processes."""
+    pri = _priors_dict(wl["priors"])
+    W = wl["W"]
+    pool.map(_oracle_walker, [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(cores)])  # imports
+    t0 = time.perf_counter()
+    pool.map(_oracle_walker, [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(cores)])
+    per_walker = (time.perf_counter() - t0)  # one walker per core, in parallel
+    if nwalk is None:
+        nwalk = int(max(cores, min(4 * W, budget_s / max(per_walker, 1e-6) * cores)))
+    jobs = [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(nwalk)]
+    t0 = time.perf_counter()
+    pool.map(_oracle_walker, jobs, chunksize=max(1, nwalk // (cores * 4)))
+    dt = time.perf_counter() - t0
+    return nwalk * wl["N"] / dt, nwalk, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (NumPy oracle port,
+    multiprocessing pool like emcee's threads=) on this box's host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    wl = make_workload(args.workload)
+    cores = len(os.sched_getaffinity(0))
+    pool = mp.Pool(cores)
+    # size each step so that warmup+steps finish within ~2 minutes
+    pri = _priors_dict(wl["priors"])
+    pool.map(_oracle_walker, [(wl["pos"][i % wl["W"]], wl["lc"], pri, wl["S"]) for i in range(cores)])  # imports
+    t0 = time.perf_counter()
+    pool.map(_oracle_walker, [(wl["pos"][i % wl["W"]], wl["lc"], pri, wl["S"]) for i in range(cores)])
+    per = time.perf_counter() - t0
+    total_steps = args.steps + args.warmup
+    nwalk = int(max(cores, min(wl["W"], (100.0 / total_steps) / max(per, 1e-6) * cores)))
+    for _ in range(args.warmup):
+        cpu_reference_rate(wl, 0, pool, cores, nwalk=nwalk)
+    t_begin = time.perf_counter()
+    rates = []
+    for _ in range(args.steps):
+        r, _, _ = cpu_reference_rate(wl, 0, pool, cores, nwalk=nwalk)
+        rates.append(r)
+    elapsed = time.perf_counter() - t_begin
+    pool.close()
+    value = args.steps * nwalk * wl["N"] / elapsed
+    sample = "%d of %d walkers per step (full N=%d, S=%d), NumPy oracle in a %d-process pool" % (
+        nwalk, wl["W"], wl["N"], wl["S"], cores)
+    line = {
+        "impl": "reference", "metric": "lnprob_walker_timestamp_evals_per_sec", "value": value, "unit": "wt/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[args.workload], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "wt/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "wt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import namaste_b200 as nb
+
+    wl = make_workload(args.workload, seed_offset=rank)
+    W, N, S = wl["W"], wl["N"], wl["S"]
+    staged = nb.LightCurve(wl["lc"], oversamp=S)
+    d_pos = torch.from_numpy(wl["pos"]).cuda()
+    d_pri = torch.from_numpy(wl["priors"]).cuda()[None].contiguous()
+    out = torch.empty((1, W), dtype=torch.float64, device="cuda")
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def device_loop(mode, steps, sampler=None):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_begin = time.perf_counter()
+        for e0, e1 in evs:
+            flush.zero_()                      # L2 flush between timed iterations (not timed)
+            e0.record(stream)
+            staged.lnprob_device(d_pos, d_pri, out=out, mode=mode)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_end = time.perf_counter()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        return ms, t_begin, t_end
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- device-resident measurement (brute force = `value`) ---------------------------------
+    device_loop("brute", max(args.warmup, 3))
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = nb.launch_count()
+    ms_brute, t_b, t_e = device_loop("brute", args.steps)
+    launches = nb.launch_count() - l0
+    # keep the same loop running ~1 s longer so nvidia-smi (100 ms period) sees it under load
+    t_stop = time.perf_counter() + (0.0 if args.profile else 1.0)
+    while time.perf_counter() < t_stop:
+        for _ in range(200):
+            staged.lnprob_device(d_pos, d_pri, out=out, mode="brute")
+        torch.cuda.synchronize()
+    clk = clocks.stop(t_b, time.perf_counter())
+    ms_brute = max_over_ranks(ms_brute)
+    device_loop("windowed", max(args.warmup, 3))
+    ms_win, _, _ = device_loop("windowed", args.steps)
+    ms_win = max_over_ranks(ms_win)
+    ref_out = out.cpu().numpy().copy()
+
+    # ---- end to end through the public host API (numpy in / numpy out) -----------------------
+    def e2e_loop(mode, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = staged.lnprob(wl["pos"], wl["priors"], mode=mode)
+        dt = time.perf_counter() - t0
+        return max_over_ranks(dt), res
+
+    e2e_loop("brute", max(args.warmup, 3))
+    dt_e2e, res_host = e2e_loop("brute", args.steps)
+    e2e_loop("windowed", max(args.warmup, 3))
+    dt_e2e_win, res_host_w = e2e_loop("windowed", args.steps)
+    assert np.allclose(res_host_w, ref_out[0], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.allclose(res_host, ref_out[0], rtol=1e-12, atol=0, equal_nan=True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    units = W * N * world
+    value = units / (ms_brute / args.steps * 1e-3)
+    flops, (m, m_int, m_edge) = algorithmic_flops(wl)
+    peak_tf, _ = nb.measure_fp64_peak()
+    achieved_tf = flops / (ms_brute / args.steps * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "lnprob_walker_timestamp_evals_per_sec", "value": value, "unit": "wt/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_brute / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[args.workload], "N": N, "S": S, "W": W,
+                   "step": "one full-ensemble lnprob evaluation (likelihood + priors), brute-force kernel",
+                   "parallelism": "independent candidate per GPU, no collective" if world > 1 else "single GPU",
+                   "l2": "192 MiB buffer zeroed between timed iterations (inputs are 0.15 MB, L2/SMEM resident by design)"},
+        "clocks": clk,
+        "e2e": {"value": units / (dt_e2e / args.steps), "unit": "wt/s",
+                "h2d_bytes_per_step": int(W * 6 * 8 + 36 * 8), "d2h_bytes_per_step": int(W * 8),
+                "ms_per_step": 1e3 * dt_e2e / args.steps,
+                "note": "LightCurve.lnprob(numpy params) -> numpy lnprob; light curve staged once like emcee args="},
+        "gpu_launches": int(launches),
+        "windowed": {"value": units / (ms_win / args.steps * 1e-3), "unit": "wt/s",
+                     "ms_per_step": ms_win / args.steps, "speedup_vs_brute": ms_brute / ms_win,
+                     "e2e": units / (dt_e2e_win / args.steps),
+                     "note": "exact prefix-sum + in-transit-window kernel; effective wt/s, not a roofline figure"},
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": traffic,
+                     "peak_source": "DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 entry)",
+                     "flops_per_launch": flops,
+                     "flops_convention": "SURVEY.md 8(d): 7/fine sample + 143 interior + 180 ingress + 5/timestamp + 40/walker",
+                     "fine_samples": m, "interior": m_int, "edge": m_edge},
+    }
+    if world == 1 and not args.no_cpu and not args.profile:
+        import multiprocessing as mp
+        cores = len(os.sched_getaffinity(0))
+        pool = mp.Pool(cores)
+        rate, nwalk, dt = cpu_reference_rate(wl, 12.0, pool, cores)
+        pool.close()
+        line["cpu_baseline"] = {"value": rate, "unit": "wt/s", "cores": cores, "kind": "port",
+                                "sample": "%d walker evaluations of the same workload (N=%d, S=%d) in %.1f s, "
+                                          "NumPy oracle in a %d-process pool" % (nwalk, N, S, dt, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="k2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: no clock-sampling continuation, no cpu_baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
