@@ -44,6 +44,7 @@ extern "C" {
 /* evaluation strategy (results agree to rounding) */
 #define NMB_MODE_BRUTE 0    /* every fine sample of every timestamp is visited            */
 #define NMB_MODE_WINDOWED 1 /* exact: out-of-transit chi^2 from prefix sums, window only  */
+#define NMB_MODE_FUSED 2    /* brute force in one launch (small problems / diagnostics)     */
 
 /* arithmetic type of the transit model */
 #define NMB_F64 64

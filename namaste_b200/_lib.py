@@ -10,9 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnamaste_b200.so")
 
 NMB_OK, NMB_ERR_ARG, NMB_ERR_CUDA, NMB_ERR_PRECOND, NMB_ERR_NAN = 0, -1, -2, -3, -4
-MODE_BRUTE, MODE_WINDOWED = 0, 1
+MODE_BRUTE, MODE_WINDOWED, MODE_FUSED = 0, 1, 2
 F64, F32 = 64, 32
-MODES = {"brute": MODE_BRUTE, "windowed": MODE_WINDOWED, MODE_BRUTE: MODE_BRUTE, MODE_WINDOWED: MODE_WINDOWED}
+MODES = {"brute": MODE_BRUTE, "windowed": MODE_WINDOWED, "fused": MODE_FUSED,
+         MODE_BRUTE: MODE_BRUTE, MODE_WINDOWED: MODE_WINDOWED, MODE_FUSED: MODE_FUSED}
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int64_p = ctypes.POINTER(ctypes.c_int64)

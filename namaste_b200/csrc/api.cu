@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "../../include/namaste_b200.h"
-#include "lnprob_kernels.cuh"
+#include "eval_pipeline.cuh"
 
 namespace {
 
@@ -42,10 +42,13 @@ struct nmb_lc {
     std::vector<double> cad;
     double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
     long long* d_n = nullptr;
-    // reduction workspace (grown on demand)
+    // reduction workspace of the fused kernel (grown on demand)
     double* d_partials = nullptr;
     int* d_tickets = nullptr;
     size_t partials_cap = 0, tickets_cap = 0;
+    // workspace of the two-stage pipeline (grown on demand)
+    nmb::EvalWs ws{};
+    size_t ws_cw = 0, ws_partials = 0;
     // staging for the host-buffer entry point
     double *h_pin = nullptr, *d_stage = nullptr;
     size_t pin_cap = 0, stage_cap = 0;
@@ -67,6 +70,9 @@ extern "C" void nmb_lc_destroy(nmb_lc* lc) {
     if (!lc) return;
     cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
     cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
+    cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.wcs); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
+    cudaFree(lc->ws.blkstart); cudaFree(lc->ws.itemwalker); cudaFree(lc->ws.itempart); cudaFree(lc->ws.itemsdone);
+    cudaFree(lc->ws.grouptick); cudaFree(lc->ws.counters);
     if (lc->h_pin) cudaFreeHost(lc->h_pin);
     if (lc->own_stream) cudaStreamDestroy(lc->own_stream);
     delete lc;
@@ -193,11 +199,119 @@ int set_smem(K kernel, size_t bytes) {
     return NMB_OK;
 }
 
+constexpr int kEvalThreads = 128;
+
+int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
+    nmb::EvalWs& ws = lc->ws;
+    if (CW > lc->ws_cw) {
+        cudaFree(ws.oot); cudaFree(ws.wcs); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.blkstart);
+        cudaFree(ws.itemwalker); cudaFree(ws.itempart); cudaFree(ws.itemsdone); cudaFree(ws.grouptick);
+        cudaFree(ws.counters);
+        ws = nmb::EvalWs{};
+        cudaFree(lc->ws.partials);
+        lc->ws.partials = nullptr;
+        lc->ws_cw = 0; lc->ws_partials = 0;
+        const int maxch = (int)std::min<size_t>(256, std::max<size_t>(1, (size_t)4194304 / CW));
+        ws.maxch = maxch;
+        CU(cudaMalloc(&ws.oot, CW * sizeof(double)));
+        CU(cudaMalloc(&ws.wcs, CW * sizeof(nmb::WalkerConsts)));
+        CU(cudaMalloc(&ws.rlo, CW * sizeof(int)));
+        CU(cudaMalloc(&ws.rhi, CW * sizeof(int)));
+        CU(cudaMalloc(&ws.itemsdone, CW * sizeof(int)));
+        CU(cudaMalloc(&ws.blkstart, (CW + 1) * sizeof(int)));
+        CU(cudaMalloc(&ws.itemwalker, CW * maxch * sizeof(int)));
+        CU(cudaMalloc(&ws.itempart, CW * maxch * sizeof(double)));
+        CU(cudaMalloc(&ws.grouptick, CW * sizeof(int)));
+        CU(cudaMalloc(&ws.counters, 2 * sizeof(int)));
+        CU(cudaMemsetAsync(ws.grouptick, 0, CW * sizeof(int), st));
+        CU(cudaMemsetAsync(ws.counters, 0, 2 * sizeof(int), st));
+        nmb::init_ranges_kernel<<<(unsigned)((CW + 255) / 256), 256, 0, st>>>(ws.rlo, ws.rhi, ws.itemsdone, (int)CW);
+        g_launches++;
+        CU(cudaGetLastError());
+        lc->ws_cw = CW;
+    }
+    if (CW * ntiles > lc->ws_partials) {
+        cudaFree(ws.partials);
+        ws.partials = nullptr; lc->ws_partials = 0;
+        CU(cudaMalloc(&ws.partials, CW * ntiles * sizeof(double)));
+        lc->ws_partials = CW * ntiles;
+    }
+    return NMB_OK;
+}
+
+// timestamps a warp evaluates per pass (TSW) and per work item (item_ts) for supersampling S:
+// smallest TSW whose S*TSW samples fill >= 90% of the 32-lane rounds they occupy
+struct EvalShape { int tsw, item_ts; };
+EvalShape eval_shape(int S) {
+    int best = 32;
+    for (int t = 1; t <= nmb::kMaxTSW; ++t) {
+        const int ns = t * S, rounds = (ns + 31) / 32;
+        if (ns >= 0.9 * rounds * 32) { best = t; break; }
+    }
+    int item = best;
+    while (item * S < 64) item += best;
+    return {best, item};
+}
+
+template <int S>
+int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                cudaStream_t st) {
+    auto kern = nmb::eval_ranges_kernel<S, kEvalThreads, 4, true>;
+    const size_t smem = sizeof(nmb::EvalSmem<S, kEvalThreads>);
+    static thread_local int grid = 0;
+    if (!grid) {
+        if (int rc = set_smem(kern, smem)) return rc;
+        int dev = 0, sms = 0, per_sm = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEvalThreads, smem));
+        grid = sms * std::max(per_sm, 1);
+    }
+    kern<<<grid, kEvalThreads, smem, st>>>(lc->view(), params, W, priors, lc->ws, eval_shape(lc->S).tsw, lnprob,
+                                           loglike);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
+}
+
 template <int S>
 int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                  cudaStream_t st) {
     const int ntiles = (int)(lc->npad / kTile);
-    // walkers per block: reuse of the staged tile vs. enough blocks to fill 148 SMs several times over
+    const size_t CW = (size_t)lc->ncand * W;
+    if (int rc = ensure_ws(lc, CW, ntiles, st)) return rc;
+    // walkers per block: reuse of the staged tile vs. enough blocks to fill 148 SMs
+    const long long blocks1 = (long long)ntiles * W * lc->ncand;
+    const int WT = (int)std::min<long long>(nmb::kWTMax, std::max<long long>(1, blocks1 / (148 * 6)));
+    const int groups = (W + WT - 1) / WT;
+    auto kern = nmb::sweep_classify_kernel<S, kThreads, kTPT, 4>;
+    const size_t smem = sizeof(nmb::ClassifySmem<S, kThreads, kTPT>);
+    if (int rc = set_smem(kern, smem)) return rc;
+    dim3 grid(ntiles, groups, (unsigned)lc->ncand);
+    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, WT, priors, lc->ws, eval_shape(lc->S).item_ts, lnprob,
+                                       loglike);
+    g_launches++;
+    CU(cudaGetLastError());
+    return launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+}
+
+template <int S>
+int launch_window(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                  cudaStream_t st) {
+    const size_t CW = (size_t)lc->ncand * W;
+    if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
+    const int wpb = kThreads / 32;
+    nmb::window_ranges_kernel<kThreads><<<(unsigned)((CW + wpb - 1) / wpb), kThreads, 0, st>>>(
+        lc->view(), params, W, priors, lc->ws, eval_shape(lc->S).item_ts, lnprob, loglike);
+    g_launches++;
+    CU(cudaGetLastError());
+    return launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+}
+
+template <int S>
+int launch_fused(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                 cudaStream_t st) {
+    const int ntiles = (int)(lc->npad / kTile);
     long long blocks1 = (long long)ntiles * W * lc->ncand;
     int WT = (int)std::min<long long>(nmb::kWTMax, std::max<long long>(1, blocks1 / (148 * 8)));
     const int groups = (W + WT - 1) / WT;
@@ -213,7 +327,7 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
         cudaFree(lc->d_tickets);
         lc->d_tickets = nullptr; lc->tickets_cap = 0;
         CU(cudaMalloc(&lc->d_tickets, need_t * sizeof(int)));
-        CU(cudaMemset(lc->d_tickets, 0, need_t * sizeof(int)));
+        CU(cudaMemsetAsync(lc->d_tickets, 0, need_t * sizeof(int), st));
         lc->tickets_cap = need_t;
     }
     auto kern = nmb::lnprob_sweep_kernel<S, kThreads, kTPT, false>;
@@ -222,19 +336,6 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     dim3 grid(ntiles, groups, (unsigned)lc->ncand);
     kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, WT, priors, lc->d_partials, lc->d_tickets, lnprob,
                                        loglike, nullptr, 0);
-    g_launches++;
-    CU(cudaGetLastError());
-    return NMB_OK;
-}
-
-template <int S>
-int launch_window(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                  cudaStream_t st) {
-    auto kern = nmb::lnprob_window_kernel<S, kThreads>;
-    const size_t smem = sizeof(nmb::WindowSmem<S, kThreads>);
-    if (int rc = set_smem(kern, smem)) return rc;
-    dim3 grid(W, (unsigned)lc->ncand);
-    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, priors, lnprob, loglike);
     g_launches++;
     CU(cudaGetLastError());
     return NMB_OK;
@@ -277,6 +378,8 @@ extern "C" int nmb_lnprob(nmb_lc* lc, const double* params, int64_t W, const dou
         NMB_DISPATCH_S(lc->S, rc = launch_sweep<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
     } else if (mode == NMB_MODE_WINDOWED) {
         NMB_DISPATCH_S(lc->S, rc = launch_window<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
+    } else if (mode == NMB_MODE_FUSED) {
+        NMB_DISPATCH_S(lc->S, rc = launch_fused<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
     } else {
         return fail(NMB_ERR_ARG, "nmb_lnprob: unknown mode");
     }

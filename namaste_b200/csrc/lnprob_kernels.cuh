@@ -47,6 +47,7 @@ __device__ __forceinline__ WalkerConsts make_walker_consts(const double* par, in
     w.b2 = par[1] * par[1];  // self.b**2
     w.vel = par[2];
     w.q = make_quad_consts(par[3], par[4], par[5]);
+    finish_quad_consts(w.q);
     // rounding slack: q_fma and q_faithful differ by < 2 ulp, sqrt rounds by 1/2 ulp
     w.qthr = (w.q.p == 0.0) ? -1.0 : (w.q.onep * w.q.onep) * (1.0 + 16 * kEps);
     double tmp[32];

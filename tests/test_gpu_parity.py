@@ -54,7 +54,7 @@ def test_occultquad_all_cases(nb):
     print("occultquad worst abs deviation:", worst)
 
 
-@pytest.mark.parametrize("mode", ["brute", "windowed"])
+@pytest.mark.parametrize("mode", ["brute", "windowed", "fused"])
 def test_logged_known_answers(nb, mode):
     g = load_golden("kat_epic203311200")
     pri = priors_from_table(g["priors"])
@@ -68,7 +68,7 @@ def test_logged_known_answers(nb, mode):
 
 @pytest.mark.parametrize("name", ["config1_epic203311200", "synth_k2_s11", "synth_kepler_s15",
                                   "synth_tess_s10", "synth_tess_s1"])
-@pytest.mark.parametrize("mode", ["brute", "windowed"])
+@pytest.mark.parametrize("mode", ["brute", "windowed", "fused"])
 def test_lnprob_fixtures(nb, name, mode):
     g = load_golden(name)
     S = int(g["oversamp"]) if "oversamp" in g.files else 10
@@ -129,7 +129,7 @@ def test_brute_vs_windowed_vs_oracle_random_box(nb):
     pri = priors_from_table(tab)
     ref = o.lnprob_ensemble(pos, lc, pri)
     staged = nb.LightCurve(lc, oversamp=10)
-    for mode in ("brute", "windowed"):
+    for mode in ("brute", "windowed", "fused"):
         got = staged.lnprob(pos, pri, mode=mode)
         assert rel(got, ref).max() < LNPROB_RTOL_TIGHT, mode
     assert np.allclose(nb.MonoOnlyLogProb(pos, lc, pri), ref, rtol=LNPROB_RTOL_TIGHT, atol=0)
