@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,9 @@ struct nmb_lc {
     std::vector<double> cad;
     double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
     long long* d_n = nullptr;
+    int *d_tgrid = nullptr, *d_gcount = nullptr;
+    double *d_t0 = nullptr, *d_ginv = nullptr;
+    int64_t gstride = 0;
     // reduction workspace of the fused kernel (grown on demand)
     double* d_partials = nullptr;
     int* d_tickets = nullptr;
@@ -58,6 +62,7 @@ struct nmb_lc {
         nmb::LcView v;
         v.t = d_t; v.f = d_f; v.w = d_w; v.pre_hi = d_pre_hi; v.pre_lo = d_pre_lo; v.off = d_off;
         v.n = d_n; v.npad = npad; v.ncand = (int)ncand; v.S = S;
+        v.tgrid = d_tgrid; v.t0 = d_t0; v.ginv = d_ginv; v.gcount = d_gcount; v.gstride = gstride;
         return v;
     }
 };
@@ -69,10 +74,11 @@ extern "C" int64_t nmb_launch_count(void) { return g_launches.load(); }
 extern "C" void nmb_lc_destroy(nmb_lc* lc) {
     if (!lc) return;
     cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
+    cudaFree(lc->d_tgrid); cudaFree(lc->d_gcount); cudaFree(lc->d_t0); cudaFree(lc->d_ginv);
     cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
-    cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.wcs); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
+    cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.lp); cudaFree(lc->ws.wcs); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
     cudaFree(lc->ws.blkstart); cudaFree(lc->ws.itemwalker); cudaFree(lc->ws.itempart); cudaFree(lc->ws.itemsdone);
-    cudaFree(lc->ws.grouptick); cudaFree(lc->ws.counters);
+    cudaFree(lc->ws.grouptick); cudaFree(lc->ws.counters); cudaFree(lc->ws.tilectr);
     if (lc->h_pin) cudaFreeHost(lc->h_pin);
     if (lc->own_stream) cudaStreamDestroy(lc->own_stream);
     delete lc;
@@ -156,8 +162,38 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
         for (int64_t i = nc; i < npad; ++i) ht[c * npad + i] = tc[nc - 1];
     }
 
+    // uniform time grid (cell = one cadence, coarser if the light curve has huge gaps)
+    std::vector<double> ht0(ncand), hginv(ncand);
+    std::vector<int> hgcount(ncand);
+    std::vector<double> gwidth(ncand);
+    int64_t gstride = 0;
+    for (int64_t c = 0; c < ncand; ++c) {
+        const double* tc = t + c * stride;
+        const int64_t nc = n[c];
+        const double range = tc[nc - 1] - tc[0];
+        double g = cads[c];
+        if (!(g > 0.0) || range / g > 4.0 * (double)nc + 16.0) g = range / (4.0 * (double)nc);
+        if (!(g > 0.0)) g = 1.0;
+        gwidth[c] = g;
+        ht0[c] = tc[0];
+        hginv[c] = 1.0 / g;
+        hgcount[c] = (int)std::floor(range / g) + 2;
+        gstride = std::max<int64_t>(gstride, hgcount[c] + 1);
+    }
+    std::vector<int> hgrid(ncand * gstride, 0);
+    for (int64_t c = 0; c < ncand; ++c) {
+        const double* tc = t + c * stride;
+        const int64_t nc = n[c];
+        int64_t i = 0;
+        for (int j = 0; j <= hgcount[c]; ++j) {
+            const double edge = ht0[c] + j * gwidth[c];
+            while (i < nc && tc[i] < edge) ++i;
+            hgrid[c * gstride + j] = (int)i;
+        }
+    }
+
     nmb_lc* lc = new nmb_lc;
-    lc->ncand = ncand; lc->nmax = nmax; lc->npad = npad; lc->S = S;
+    lc->ncand = ncand; lc->nmax = nmax; lc->npad = npad; lc->S = S; lc->gstride = gstride;
     lc->n.assign(n, n + ncand);
     lc->cad = cads;
     cudaGetDevice(&lc->device);
@@ -171,6 +207,11 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
     if ((e = up(&lc->d_t, ht)) != cudaSuccess || (e = up(&lc->d_f, hf)) != cudaSuccess ||
         (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
         (e = up(&lc->d_pre_lo, hpl)) != cudaSuccess || (e = up(&lc->d_off, hoff)) != cudaSuccess ||
+        (e = up(&lc->d_t0, ht0)) != cudaSuccess || (e = up(&lc->d_ginv, hginv)) != cudaSuccess ||
+        (e = cudaMalloc(&lc->d_tgrid, hgrid.size() * sizeof(int))) != cudaSuccess ||
+        (e = cudaMemcpy(lc->d_tgrid, hgrid.data(), hgrid.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&lc->d_gcount, ncand * sizeof(int))) != cudaSuccess ||
+        (e = cudaMemcpy(lc->d_gcount, hgcount.data(), ncand * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMalloc(&lc->d_n, ncand * sizeof(long long))) != cudaSuccess ||
         (e = cudaMemcpy(lc->d_n, hn.data(), ncand * sizeof(long long), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&lc->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -201,12 +242,39 @@ int set_smem(K kernel, size_t bytes) {
 
 constexpr int kEvalThreads = 128;
 
+// NMB_STAGE_TIMING=1: time stage 1 / stage 2 separately with CUDA events (diagnostics only)
+struct StageTimer {
+    bool on = false;
+    cudaEvent_t e[3];
+    double acc1 = 0, acc2 = 0;
+    long n = 0;
+    StageTimer() {
+        on = std::getenv("NMB_STAGE_TIMING") != nullptr;
+        if (on) for (auto& x : e) cudaEventCreate(&x);
+    }
+    void mark(int i, cudaStream_t st) { if (on) cudaEventRecord(e[i], st); }
+    void done(const char* what) {
+        if (!on) return;
+        cudaEventSynchronize(e[2]);
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e[0], e[1]);
+        cudaEventElapsedTime(&b, e[1], e[2]);
+        acc1 += a; acc2 += b; ++n;
+        if (n % 100 == 0) {
+            fprintf(stderr, "[nmb stage timing] %s: stage1 %.2f us, stage2 %.2f us (mean of 100)\n", what,
+                    1e3 * acc1 / 100, 1e3 * acc2 / 100);
+            acc1 = acc2 = 0;
+        }
+    }
+};
+StageTimer g_timer;
+
 int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
     nmb::EvalWs& ws = lc->ws;
     if (CW > lc->ws_cw) {
-        cudaFree(ws.oot); cudaFree(ws.wcs); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.blkstart);
+        cudaFree(ws.oot); cudaFree(ws.lp); cudaFree(ws.wcs); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.blkstart);
         cudaFree(ws.itemwalker); cudaFree(ws.itempart); cudaFree(ws.itemsdone); cudaFree(ws.grouptick);
-        cudaFree(ws.counters);
+        cudaFree(ws.counters); cudaFree(ws.tilectr);
         ws = nmb::EvalWs{};
         cudaFree(lc->ws.partials);
         lc->ws.partials = nullptr;
@@ -214,6 +282,7 @@ int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
         const int maxch = (int)std::min<size_t>(256, std::max<size_t>(1, (size_t)4194304 / CW));
         ws.maxch = maxch;
         CU(cudaMalloc(&ws.oot, CW * sizeof(double)));
+        CU(cudaMalloc(&ws.lp, CW * sizeof(double)));
         CU(cudaMalloc(&ws.wcs, CW * sizeof(nmb::WalkerConsts)));
         CU(cudaMalloc(&ws.rlo, CW * sizeof(int)));
         CU(cudaMalloc(&ws.rhi, CW * sizeof(int)));
@@ -222,9 +291,12 @@ int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
         CU(cudaMalloc(&ws.itemwalker, CW * maxch * sizeof(int)));
         CU(cudaMalloc(&ws.itempart, CW * maxch * sizeof(double)));
         CU(cudaMalloc(&ws.grouptick, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.counters, 2 * sizeof(int)));
+        CU(cudaMalloc(&ws.counters, 4 * sizeof(int)));
+        CU(cudaMalloc(&ws.tilectr, (size_t)lc->ncand * (lc->npad / kTile) * sizeof(int)));
+        ws.ntilectr = (int)(lc->ncand * (lc->npad / kTile));
+        CU(cudaMemsetAsync(ws.tilectr, 0, (size_t)ws.ntilectr * sizeof(int), st));
         CU(cudaMemsetAsync(ws.grouptick, 0, CW * sizeof(int), st));
-        CU(cudaMemsetAsync(ws.counters, 0, 2 * sizeof(int), st));
+        CU(cudaMemsetAsync(ws.counters, 0, 4 * sizeof(int), st));
         nmb::init_ranges_kernel<<<(unsigned)((CW + 255) / 256), 256, 0, st>>>(ws.rlo, ws.rhi, ws.itemsdone, (int)CW);
         g_launches++;
         CU(cudaGetLastError());
@@ -242,21 +314,27 @@ int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
 // timestamps a warp evaluates per pass (TSW) and per work item (item_ts) for supersampling S:
 // smallest TSW whose S*TSW samples fill >= 90% of the 32-lane rounds they occupy
 struct EvalShape { int tsw, item_ts; };
-EvalShape eval_shape(int S) {
+EvalShape eval_shape(int S, size_t CW) {
     int best = 32;
     for (int t = 1; t <= nmb::kMaxTSW; ++t) {
         const int ns = t * S, rounds = (ns + 31) / 32;
         if (ns >= 0.9 * rounds * 32) { best = t; break; }
     }
+    // item size: about three items per resident warp for a typical ~40-timestamp transit, so that
+    // small ensembles are spread over the GPU and large ones keep one item per walker
+    const double want = 40.0 * (double)CW / (3.0 * 148 * 16);
     int item = best;
-    while (item * S < 64) item += best;
+    while (item * S < 64 || item < want) item += best;
+    if (item > 64 * best) item = 64 * best;
+    static const int force = std::getenv("NMB_ITEM_TS") ? std::atoi(std::getenv("NMB_ITEM_TS")) : 0;
+    if (force > 0) item = (force + best - 1) / best * best;
     return {best, item};
 }
 
-template <int S>
-int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                cudaStream_t st) {
-    auto kern = nmb::eval_ranges_kernel<S, kEvalThreads, 4, true>;
+template <int S, int MINB>
+int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                   cudaStream_t st) {
+    auto kern = nmb::eval_ranges_kernel<S, kEvalThreads, MINB, true>;
     const size_t smem = sizeof(nmb::EvalSmem<S, kEvalThreads>);
     static thread_local int grid = 0;
     if (!grid) {
@@ -267,32 +345,60 @@ int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, d
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEvalThreads, smem));
         grid = sms * std::max(per_sm, 1);
     }
-    kern<<<grid, kEvalThreads, smem, st>>>(lc->view(), params, W, priors, lc->ws, eval_shape(lc->S).tsw, lnprob,
-                                           loglike);
+    kern<<<grid, kEvalThreads, smem, st>>>(lc->view(), params, W, priors, lc->ws,
+                                           eval_shape(lc->S, (size_t)lc->ncand * W).tsw, lnprob, loglike);
     g_launches++;
     CU(cudaGetLastError());
     return NMB_OK;
 }
 
 template <int S>
+int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                cudaStream_t st) {
+    static const int mb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 4;
+    if (mb == 6) return launch_eval_mb<S, 6>(lc, params, W, priors, lnprob, loglike, st);
+    if (mb == 5) return launch_eval_mb<S, 5>(lc, params, W, priors, lnprob, loglike, st);
+    if (mb == 3) return launch_eval_mb<S, 3>(lc, params, W, priors, lnprob, loglike, st);
+    return launch_eval_mb<S, 4>(lc, params, W, priors, lnprob, loglike, st);
+}
+
+template <int S>
 int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                  cudaStream_t st) {
+    constexpr int WT = 8, MINB = 4;
+    constexpr int kBlock = kThreads + 32;  // 4 consumer warps + 1 producer warp
     const int ntiles = (int)(lc->npad / kTile);
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, ntiles, st)) return rc;
-    // walkers per block: reuse of the staged tile vs. enough blocks to fill 148 SMs
-    const long long blocks1 = (long long)ntiles * W * lc->ncand;
-    const int WT = (int)std::min<long long>(nmb::kWTMax, std::max<long long>(1, blocks1 / (148 * 6)));
     const int groups = (W + WT - 1) / WT;
-    auto kern = nmb::sweep_classify_kernel<S, kThreads, kTPT, 4>;
-    const size_t smem = sizeof(nmb::ClassifySmem<S, kThreads, kTPT>);
-    if (int rc = set_smem(kern, smem)) return rc;
-    dim3 grid(ntiles, groups, (unsigned)lc->ncand);
-    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, WT, priors, lc->ws, eval_shape(lc->S).item_ts, lnprob,
-                                       loglike);
+    auto kern = nmb::sweep_classify_kernel<S, kThreads, kTPT, WT, MINB>;
+    const size_t smem = sizeof(nmb::ClassifySmem<S, kThreads, kTPT, WT>);
+    static thread_local int slots = 0;
+    if (!slots) {
+        if (int rc = set_smem(kern, smem)) return rc;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int dev = 0, sms = 0, per_sm = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+        slots = sms * std::max(per_sm, 1);
+    }
+    // one resident wave: blocks of a tile share its queue of walker groups
+    const long long per_tile = std::max<long long>(1, slots / ((long long)ntiles * lc->ncand));
+    const int by = (int)std::min<long long>(groups, per_tile);
+    dim3 grid(ntiles, by, (unsigned)lc->ncand);
+    g_timer.mark(0, st);
+    nmb::walker_setup_kernel<<<(unsigned)((CW + 63) / 64), 64, 0, st>>>(lc->view(), params, W, priors, lc->ws);
+    g_launches++;
+    kern<<<grid, kBlock, smem, st>>>(lc->view(), params, W, groups, priors, lc->ws,
+                                       eval_shape(lc->S, CW).item_ts, lnprob, loglike);
     g_launches++;
     CU(cudaGetLastError());
-    return launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+    g_timer.mark(1, st);
+    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+    g_timer.mark(2, st);
+    g_timer.done("brute");
+    return rc;
 }
 
 template <int S>
@@ -300,12 +406,17 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
                   cudaStream_t st) {
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
-    const int wpb = kThreads / 32;
-    nmb::window_ranges_kernel<kThreads><<<(unsigned)((CW + wpb - 1) / wpb), kThreads, 0, st>>>(
-        lc->view(), params, W, priors, lc->ws, eval_shape(lc->S).item_ts, lnprob, loglike);
+    constexpr int kWinThreads = 64;
+    g_timer.mark(0, st);
+    nmb::window_ranges_kernel<kWinThreads><<<(unsigned)((CW + kWinThreads - 1) / kWinThreads), kWinThreads, 0, st>>>(
+        lc->view(), params, W, priors, lc->ws, eval_shape(lc->S, (size_t)lc->ncand * W).item_ts, lnprob, loglike);
     g_launches++;
     CU(cudaGetLastError());
-    return launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+    g_timer.mark(1, st);
+    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+    g_timer.mark(2, st);
+    g_timer.done("windowed");
+    return rc;
 }
 
 template <int S>

@@ -31,6 +31,7 @@ namespace nmb {
 struct EvalWs {
     double* partials;    // [CW][ntiles]   out-of-transit chi^2 per (walker, tile)      (brute)
     double* oot;         // [CW]           out-of-transit chi^2 per walker
+    double* lp;          // [CW]           log-prior per walker (computed in stage 1)
     WalkerConsts* wcs;   // [CW]
     int* rlo;            // [CW]  first in-transit timestamp   (INT_MAX when idle)
     int* rhi;            // [CW]  one past the last            (0 when idle)
@@ -39,7 +40,10 @@ struct EvalWs {
     double* itempart;    // [CW*maxch]
     int* itemsdone;      // [CW]  (0 when idle)
     int* grouptick;      // [C*ngroups] (0 when idle)
-    int* counters;       // [0] groups/blocks finished (0 when idle), [1] total items of this launch
+    int* counters;       // [0] groups/blocks finished (0 when idle), [1] total items of this launch,
+                         // [2] next item of the stage-2 queue
+    int* tilectr;        // [C*ntiles] next walker group of each tile (reset by stage 2)
+    int ntilectr;
     int maxch;
 };
 
@@ -103,41 +107,67 @@ __device__ void scan_items(const EvalWs& ws, int CW, int item_ts, int* s_scan /*
         ws.blkstart[CW] = running;
         ws.counters[1] = running;
         ws.counters[0] = 0;
+        ws.counters[2] = 0;
     }
 }
 
-template <int S, int THREADS, int TPT>
+// named barriers (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int S, int CTHREADS, int TPT, int WT>
 struct ClassifySmem {
-    static constexpr int TT = THREADS * TPT;
+    static constexpr int TT = CTHREADS * TPT;
     double t[TT], f[TT], w[TT];
-    double warpsum[kWTMax][THREADS / 32];
+    double warpsum[2][WT][CTHREADS / 32];
     double off[kMaxS];
-    WalkerConsts wc[kWTMax];
+    // per-walker classification constants, structure-of-arrays, double buffered across groups
+    double vel[2][WT], nvtc[2][WT], b2[2][WT], fbar[2][WT];
+    int qhi[2][WT];
     unsigned long long mbar;
-    int s_scan[THREADS / 32 + 1];
-    int last;
+    int group[2];
+    int s_scan[CTHREADS / 32 + 2];
+    int doscan;
 };
 
-template <int S, int THREADS, int TPT, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int WT, const double* __restrict__ priors,
-                      EvalWs ws, int item_ts, double* __restrict__ lnprob, double* __restrict__ loglike) {
-    constexpr int TT = THREADS * TPT;
-    constexpr int NWARP = THREADS / 32;
+// Brute-force stage 1, warp specialised.  A block owns one time tile (staged once by TMA) and
+// pulls walker groups from the tile's queue.
+//   producer warp (the last one): fetches the next group, derives its walkers' constants one
+//     group ahead of the consumers, later publishes the group's tile partials, and - when this
+//     was the group's last tile - folds the tiles, evaluates the priors and settles walkers that
+//     never transit;
+//   consumer warps: per thread and timestamp the S fine times ft_k = t_i + off_k are formed once
+//     per group and shared by its WT walkers; per walker and fine sample the sweep costs two DFMA
+//     and one DSETP:  vx' = fma(vel, ft_k, -vel*tcen), q' = fma(vx', vx', b^2), outside iff
+//     q' > qthr_c.  They never wait for constants or reductions of other groups.
+template <int S, int CTHREADS, int TPT, int WT, int MINB>
+__global__ void __launch_bounds__(CTHREADS + 32, MINB)
+sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int ngroups,
+                      const double* __restrict__ priors, EvalWs ws, int item_ts, double* __restrict__ lnprob,
+                      double* __restrict__ loglike) {
+    constexpr int TT = CTHREADS * TPT;
+    constexpr int NCW = CTHREADS / 32;  // consumer warps
+    constexpr int ALL = CTHREADS + 32;
+    constexpr int SR = S > 0 ? S : kMaxS;
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 3;  // +buf
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ClassifySmem<S, THREADS, TPT>& sm = *reinterpret_cast<ClassifySmem<S, THREADS, TPT>*>(smem_raw);
+    ClassifySmem<S, CTHREADS, TPT, WT>& sm = *reinterpret_cast<ClassifySmem<S, CTHREADS, TPT, WT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, group = blockIdx.y, cand = blockIdx.z;
-    const int ngroups = gridDim.y, ntiles = gridDim.x;
+    const int tile = blockIdx.x, cand = blockIdx.z;
+    const int ntiles = gridDim.x;
     const int Sx = s_of<S>(lc.S);
     const long long n = lc.n[cand];
     const long long base = (long long)tile * TT;
-    // walkers are dealt to groups round-robin so that neighbouring (similar) walkers do not pile
-    // up in one block: walker = wl * ngroups + group
-    const int nw = (W - group + ngroups - 1) / ngroups < WT ? (W - group + ngroups - 1) / ngroups : WT;
+    const bool live = base < n;  // tiles past this candidate's end only contribute zeros
+    int* ctr = ws.tilectr + (long long)cand * ntiles + tile;
 
-    if (base < n) {
-        if (tid == 0) {
+    if (tid == 0) {
+        sm.doscan = 0;
+        if (live) {
             mbar_init(&sm.mbar, 1);
             mbar_expect_tx(&sm.mbar, 3u * TT * sizeof(double));
             const long long g = (long long)cand * lc.npad + base;
@@ -145,143 +175,250 @@ sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int W
             tma_bulk_g2s(sm.f, lc.f + g, TT * sizeof(double), &sm.mbar);
             tma_bulk_g2s(sm.w, lc.w + g, TT * sizeof(double), &sm.mbar);
         }
-        if (tid < Sx) sm.off[tid] = lc.off[(long long)cand * Sx + tid];
-        if (tid < nw) {
-            const long long cw = (long long)cand * W + tid * ngroups + group;
-            sm.wc[tid] = make_walker_consts(params + cw * 6, Sx);
-            if (tile == 0) ws.wcs[cw] = sm.wc[tid];
-        }
-        __syncthreads();
-        mbar_wait(&sm.mbar, 0);
+    }
+    if (tid < Sx) sm.off[tid] = lc.off[(long long)cand * Sx + tid];
+    __syncthreads();
 
-        double ti[TPT], fi[TPT], wi[TPT];
-        bool valid[TPT];
+    if (warp == NCW) {
+        // ------------------------------- producer ------------------------------------------
+        int pend_group[2] = {-1, -1};
+        for (int it = 0;; ++it) {
+            const int buf = it & 1;
+            if (it >= 2) {
+                bar_sync(BAR_EMPTY + buf, ALL);  // consumers finished group it-2: its warp sums are in smem
+                const int group = pend_group[buf];
+                const int nw_all = (W - group + ngroups - 1) / ngroups;
+                const int nw = nw_all < WT ? nw_all : WT;
+                if (lane < nw) {
+                    double sacc = 0.0;
+                    if (live) {
 #pragma unroll
-        for (int s = 0; s < TPT; ++s) {
-            const int li = s * THREADS + tid;
-            valid[s] = (base + li) < n;
-            ti[s] = sm.t[li];
-            fi[s] = sm.f[li];
-            wi[s] = sm.w[li];
-        }
-        double off[S > 0 ? S : 1];
-        if (S > 0) {
-#pragma unroll
-            for (int k = 0; k < S; ++k) off[k] = sm.off[k];
-        }
-
-        for (int wl = 0; wl < nw; ++wl) {
-            const double tcen = sm.wc[wl].tcen, vel = sm.wc[wl].vel, b2 = sm.wc[wl].b2, qthr = sm.wc[wl].qthr;
-            const double fbar = sm.wc[wl].fbar;
-            double acc = 0.0;
-            int hmin = INT_MAX, hmax = -1;
-#pragma unroll
-            for (int s = 0; s < TPT; ++s) {
-                bool hit = false;
-                if (S > 0) {
-#pragma unroll
-                    for (int k = 0; k < S; ++k) {
-                        const double vx = vel * ((ti[s] + off[k]) - tcen);
-                        hit |= !(fma(vx, vx, b2) > qthr);
+                        for (int i = 0; i < NCW; ++i) sacc += sm.warpsum[buf][lane][i];
                     }
-                } else {
-                    for (int k = 0; k < Sx; ++k) {
-                        const double vx = vel * ((ti[s] + sm.off[k]) - tcen);
-                        hit |= !(fma(vx, vx, b2) > qthr);
-                    }
+                    ws.partials[((long long)cand * W + lane * ngroups + group) * ntiles + tile] = sacc;
                 }
-                if (valid[s]) {
-                    if (hit) {
-                        const int li = s * THREADS + tid;
-                        hmin = min(hmin, li);
-                        hmax = max(hmax, li);
-                    } else {
-                        const double r = fi[s] - fbar;
-                        acc += wi[s] * (r * r);
-                    }
-                }
-            }
-            if (__any_sync(0xffffffffu, hmax >= 0)) {  // rare: this warp touches the transit
-                const int wmin = __reduce_min_sync(0xffffffffu, hmin);
-                const int wmax = __reduce_max_sync(0xffffffffu, hmax);
+                __threadfence();
+                __syncwarp();
+                int tk = 0;
                 if (lane == 0) {
-                    const long long cw = (long long)cand * W + wl * ngroups + group;
-                    atomicMin(ws.rlo + cw, (int)base + wmin);
-                    atomicMax(ws.rhi + cw, (int)base + wmax + 1);
+                    int* gt = ws.grouptick + (long long)cand * ngroups + group;
+                    tk = atomicAdd(gt, 1);
+                    if (tk == ntiles - 1) *gt = 0;
                 }
+                tk = __shfl_sync(0xffffffffu, tk, 0);
+                if (tk == ntiles - 1) {  // last tile of this group: fold tiles, priors, settle
+                    __threadfence();
+                    if (lane < nw) {
+                        const long long cw = (long long)cand * W + lane * ngroups + group;
+                        const double* row = ws.partials + cw * ntiles;
+                        double sacc = 0.0;
+                        for (int i = 0; i < ntiles; ++i) sacc += __ldcg(row + i);
+                        const int n_w = __ldcg(ws.rhi + cw) - __ldcg(ws.rlo + cw);
+                        if (n_w <= 0) {  // never in transit: done here
+                            if (loglike) loglike[cw] = sacc;
+                            lnprob[cw] = sacc + ws.lp[cw];
+                            ws.rlo[cw] = INT_MAX;
+                            ws.rhi[cw] = 0;
+                        } else {
+                            ws.oot[cw] = sacc;
+                        }
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int done = atomicAdd(ws.counters, 1);
+                        if (done == ngroups * (int)gridDim.z - 1) sm.doscan = 1;  // every group folded
+                    }
+                }
+                pend_group[buf] = -1;
             }
-            acc = warp_sum(acc);
-            if (lane == 0) sm.warpsum[wl][warp] = acc;
-        }
-        __syncthreads();
-        if (tid < nw) {
-            double s = 0.0;
+            int group = 0;
+            if (lane == 0) group = atomicAdd(ctr, 1);
+            group = __shfl_sync(0xffffffffu, group, 0);
+            const bool end = group >= ngroups;
+            if (!end) {
+                const int nw_all = (W - group + ngroups - 1) / ngroups;
+                const int nw = nw_all < WT ? nw_all : WT;
+                if (lane < WT) {
+                    if (live && lane < nw) {
+                        const WalkerConsts* wc = ws.wcs + ((long long)cand * W + lane * ngroups + group);
+                        sm.vel[buf][lane] = wc->vel; sm.nvtc[buf][lane] = wc->nvtc; sm.b2[buf][lane] = wc->b2;
+                        sm.qhi[buf][lane] = wc->qhi; sm.fbar[buf][lane] = wc->fbar;
+                    } else {  // padding walker: never in transit, result discarded
+                        sm.vel[buf][lane] = 0.0; sm.nvtc[buf][lane] = 0.0; sm.b2[buf][lane] = 0.0;
+                        sm.qhi[buf][lane] = -1; sm.fbar[buf][lane] = 1.0;
+                    }
+                }
+                pend_group[buf] = group;
+            }
+            if (lane == 0) sm.group[buf] = end ? -1 : group;
+            __syncwarp();
+            bar_arrive(BAR_FULL + buf, ALL);
+            if (end) {
+                // drain: the other buffer may still hold a group the consumers are working on
+                const int ob = buf ^ 1;
+                if (pend_group[ob] >= 0) {
+                    // reuse the loop body by running one more virtual iteration for that buffer
+                    bar_sync(BAR_EMPTY + ob, ALL);
+                    const int g2 = pend_group[ob];
+                    const int nw_all2 = (W - g2 + ngroups - 1) / ngroups;
+                    const int nw2 = nw_all2 < WT ? nw_all2 : WT;
+                    if (lane < nw2) {
+                        double sacc = 0.0;
+                        if (live) {
 #pragma unroll
-            for (int i = 0; i < NWARP; ++i) s += sm.warpsum[tid][i];
-            ws.partials[((long long)cand * W + tid * ngroups + group) * ntiles + tile] = s;
+                            for (int i = 0; i < NCW; ++i) sacc += sm.warpsum[ob][lane][i];
+                        }
+                        ws.partials[((long long)cand * W + lane * ngroups + g2) * ntiles + tile] = sacc;
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    int tk = 0;
+                    if (lane == 0) {
+                        int* gt = ws.grouptick + (long long)cand * ngroups + g2;
+                        tk = atomicAdd(gt, 1);
+                        if (tk == ntiles - 1) *gt = 0;
+                    }
+                    tk = __shfl_sync(0xffffffffu, tk, 0);
+                    if (tk == ntiles - 1) {
+                        __threadfence();
+                        if (lane < nw2) {
+                            const long long cw = (long long)cand * W + lane * ngroups + g2;
+                            const double* row = ws.partials + cw * ntiles;
+                            double sacc = 0.0;
+                            for (int i = 0; i < ntiles; ++i) sacc += __ldcg(row + i);
+                            const int n_w = __ldcg(ws.rhi + cw) - __ldcg(ws.rlo + cw);
+                            if (n_w <= 0) {
+                                if (loglike) loglike[cw] = sacc;
+                                lnprob[cw] = sacc + ws.lp[cw];
+                                ws.rlo[cw] = INT_MAX;
+                                ws.rhi[cw] = 0;
+                            } else {
+                                ws.oot[cw] = sacc;
+                            }
+                        }
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int done = atomicAdd(ws.counters, 1);
+                            if (done == ngroups * (int)gridDim.z - 1) sm.doscan = 1;
+                        }
+                    }
+                }
+                break;
+            }
         }
     } else {
-        if (tid < nw) ws.partials[((long long)cand * W + tid * ngroups + group) * ntiles + tile] = 0.0;
-    }
-
-    // ---- the last tile-block of this (candidate, group) folds the tiles of its walkers ----------
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        int* tk = ws.grouptick + (long long)cand * ngroups + group;
-        const int t = atomicAdd(tk, 1);
-        sm.last = (t == ntiles - 1);
-        if (sm.last) *tk = 0;
-    }
-    __syncthreads();
-    if (!sm.last) return;
-    __threadfence();
-    for (int wl = warp; wl < nw; wl += NWARP) {
-        const long long cw = (long long)cand * W + wl * ngroups + group;
-        const double* row = ws.partials + cw * ntiles;
-        double s = 0.0;
-        for (int i = lane; i < ntiles; i += 32) s += __ldcg(row + i);
-        s = warp_sum(s);
-        if (lane == 0) {
-            const int n_w = __ldcg(ws.rhi + cw) - __ldcg(ws.rlo + cw);
-            if (n_w <= 0) {  // never in transit: done here
-                if (loglike) loglike[cw] = s;
-                lnprob[cw] = s + (priors ? ln_prior_dev(params + cw * 6, priors + (long long)cand * 36, 6) : 0.0);
-                ws.rlo[cw] = INT_MAX;
-                ws.rhi[cw] = 0;
-            } else {
-                ws.oot[cw] = s;
+        // ------------------------------- consumers -----------------------------------------
+        if (live) mbar_wait(&sm.mbar, 0);
+        for (int it = 0;; ++it) {
+            const int buf = it & 1;
+            bar_sync(BAR_FULL + buf, ALL);
+            const int group = sm.group[buf];
+            if (group < 0) break;
+            if (live) {
+                double acc[WT];
+#pragma unroll
+                for (int wl = 0; wl < WT; ++wl) acc[wl] = 0.0;
+#pragma unroll 1
+                for (int s = 0; s < TPT; ++s) {
+                    const int li = s * CTHREADS + tid;
+                    const bool valid = (base + li) < n;
+                    const double ti = sm.t[li], fi = sm.f[li], wi = sm.w[li];
+                    const double r1 = fi - 1.0;
+                    const double term1 = wi * (r1 * r1);
+                    double ft[SR];
+                    if (S > 0) {
+#pragma unroll
+                        for (int k = 0; k < SR; ++k) ft[k] = ti + sm.off[k];
+                    }
+#pragma unroll
+                    for (int wl = 0; wl < WT; ++wl) {
+                        const double vel = sm.vel[buf][wl], nvtc = sm.nvtc[buf][wl], b2 = sm.b2[buf][wl];
+                        const int qhi = sm.qhi[buf][wl];
+                        int qmin = INT_MAX;  // smallest high word of q' over the S fine samples
+                        if (S > 0) {
+#pragma unroll
+                            for (int k = 0; k < SR; ++k) {
+                                const double vx = fma(vel, ft[k], nvtc);
+                                qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
+                            }
+                        } else {
+                            for (int k = 0; k < Sx; ++k) {
+                                const double vx = fma(vel, ti + sm.off[k], nvtc);
+                                qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
+                            }
+                        }
+                        const bool hit = (qmin <= qhi) && valid;
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (m != 0 && lane == 0) {  // rare: this warp touches the transit of walker wl
+                            const long long cw = (long long)cand * W + wl * ngroups + group;
+                            const int w0i = (int)base + s * CTHREADS + warp * 32;
+                            atomicMin(ws.rlo + cw, w0i + (__ffs(m) - 1));
+                            atomicMax(ws.rhi + cw, w0i + (32 - __clz(m)));
+                        }
+                        const double fbar = sm.fbar[buf][wl];
+                        double term = term1;
+                        if (fbar != 1.0) {  // block-uniform, practically never taken
+                            const double r = fi - fbar;
+                            term = wi * (r * r);
+                        }
+                        acc[wl] += (valid && !hit) ? term : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int wl = 0; wl < WT; ++wl) {
+                    const double v = warp_sum(acc[wl]);
+                    if (lane == 0) sm.warpsum[buf][wl][warp] = v;
+                }
             }
+            __threadfence();  // range atomics of this group are visible before the producer's ticket
+            __syncwarp();
+            bar_arrive(BAR_EMPTY + buf, ALL);
         }
     }
-    // ---- the globally last group builds the item list for stage 2 --------------------------------
-    __threadfence();
     __syncthreads();
-    if (tid == 0) {
-        const int done = atomicAdd(ws.counters, 1);
-        sm.last = (done == (int)(gridDim.y * gridDim.z) - 1);
-    }
-    __syncthreads();
-    if (!sm.last) return;
+    if (!sm.doscan) return;
     __threadfence();
-    scan_items<THREADS>(ws, W * (int)gridDim.z, item_ts, sm.s_scan);
+    scan_items<ALL>(ws, W * (int)gridDim.z, item_ts, sm.s_scan);
 }
 
-// ---- windowed stage 1 -----------------------------------------------------------------------
+// ---- per-walker setup for the brute-force sweep: constants + log-prior, one thread per walker ----
+__global__ void walker_setup_kernel(LcView lc, const double* __restrict__ params, int W,
+                                    const double* __restrict__ priors, EvalWs ws) {
+    const int cw = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cw >= W * lc.ncand) return;
+    const int cand = cw / W;
+    ws.wcs[cw] = make_walker_consts(params + (long long)cw * 6, lc.S);
+    ws.lp[cw] = priors ? ln_prior_dev(params + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
+}
+
+// ---- windowed stage 1: one thread per walker ---------------------------------------------------
+// first index i in [0, n) with t[i] >= x (UPPER = false) or t[i] > x (UPPER = true)
+template <bool UPPER>
+__device__ __forceinline__ int bsearch_t(const double* __restrict__ t, int n, double x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double v = __ldg(t + mid);
+        if (UPPER ? (v > x) : (v >= x)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors,
                      EvalWs ws, int item_ts, double* __restrict__ lnprob, double* __restrict__ loglike) {
     __shared__ int s_scan[THREADS / 32 + 1];
     __shared__ int s_last;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int CW = W * lc.ncand;
-    const int cw = blockIdx.x * (THREADS / 32) + warp;
+    const int cw = blockIdx.x * THREADS + tid;
     const int Sx = lc.S;
     if (cw < CW) {
         const int cand = cw / W;
-        const long long n = lc.n[cand];
-        const double* __restrict__ gt = lc.t + (long long)cand * lc.npad;
+        const int n = (int)lc.n[cand];
         const WalkerConsts wc = make_walker_consts(params + (long long)cw * 6, Sx);
         const double span = lc.off[(long long)cand * Sx + Sx - 1];
         const double hx2 = wc.qthr - wc.b2;
@@ -301,37 +438,44 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
                 if (!(tlo == tlo) || !(thi == thi) || isinf(tlo) || isinf(thi)) full = true;
             }
         }
-        long long ilo, ihi;
+        int ilo, ihi;
         if (full) {
             ilo = 0; ihi = n;
         } else if (empty) {
             ilo = 0; ihi = 0;
         } else {
-            ilo = max(0LL, warp_bound<false>(gt, n, tlo, lane) - 1);
-            ihi = min(n, warp_bound<true>(gt, n, thi, lane) + 1);
+            // O(1) lookup in the uniform time grid, widened by one cell on each side
+            const double t0 = lc.t0[cand], ginv = lc.ginv[cand];
+            const int gc = lc.gcount[cand];
+            const int* __restrict__ grid = lc.tgrid + (long long)cand * lc.gstride;
+            const double jl = floor((tlo - t0) * ginv) - 1.0, jh = floor((thi - t0) * ginv) + 2.0;
+            const int j0 = jl < 0.0 ? 0 : (jl > (double)gc ? gc : (int)jl);
+            const int j1 = jh < 0.0 ? 0 : (jh > (double)gc ? gc : (int)jh);
+            ilo = __ldg(grid + j0);
+            ihi = (jh > (double)gc) ? n : __ldg(grid + j1);
             if (ihi < ilo) ihi = ilo;
         }
-        if (lane == 0) {
-            // out-of-transit part: pre[ilo] + (pre[n] - pre[ihi]) in double-double
-            const double* ph = lc.pre_hi + (long long)cand * (lc.npad + 1);
-            const double* pl = lc.pre_lo + (long long)cand * (lc.npad + 1);
-            double s, e, s2, e2;
-            two_sum(ph[n], -ph[ihi], s, e);
-            e += pl[n] - pl[ihi];
-            two_sum(s, ph[ilo], s2, e2);
-            e2 += e + pl[ilo];
-            const double oot = s2 + e2;
-            if (ihi - ilo <= 0) {
-                if (loglike) loglike[cw] = oot;
-                lnprob[cw] = oot + (priors ? ln_prior_dev(params + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0);
-                ws.rlo[cw] = INT_MAX;
-                ws.rhi[cw] = 0;
-            } else {
-                ws.oot[cw] = oot;
-                ws.wcs[cw] = wc;
-                ws.rlo[cw] = (int)ilo;
-                ws.rhi[cw] = (int)ihi;
-            }
+        // out-of-transit part: pre[ilo] + (pre[n] - pre[ihi]) in double-double
+        const double* ph = lc.pre_hi + (long long)cand * (lc.npad + 1);
+        const double* pl = lc.pre_lo + (long long)cand * (lc.npad + 1);
+        double sa, ea, sb, eb;
+        two_sum(ph[n], -ph[ihi], sa, ea);
+        ea += pl[n] - pl[ihi];
+        two_sum(sa, ph[ilo], sb, eb);
+        eb += ea + pl[ilo];
+        const double oot = sb + eb;
+        const double lp = priors ? ln_prior_dev(params + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
+        if (ihi - ilo <= 0) {
+            if (loglike) loglike[cw] = oot;
+            lnprob[cw] = oot + lp;
+            ws.rlo[cw] = INT_MAX;
+            ws.rhi[cw] = 0;
+        } else {
+            ws.oot[cw] = oot;
+            ws.lp[cw] = lp;
+            ws.wcs[cw] = wc;
+            ws.rlo[cw] = ilo;
+            ws.rhi[cw] = ihi;
         }
     }
     __threadfence();
@@ -388,6 +532,22 @@ struct EvalSmem {
     double scratch[THREADS / 32][kMaxTSW * ((S > 0 ? S : kMaxS) | 1)];
 };
 
+struct ItemMeta {
+    int cw, first, nch, lo, hi;
+};
+__device__ __forceinline__ ItemMeta load_item_meta(const EvalWs& ws, int item, int total) {
+    ItemMeta m;
+    m.cw = -1; m.first = 0; m.nch = 1; m.lo = 0; m.hi = 0;
+    if (item < total) {
+        m.cw = __ldg(ws.itemwalker + item);
+        m.first = __ldcg(ws.blkstart + m.cw);
+        m.nch = __ldcg(ws.blkstart + m.cw + 1) - m.first;
+        m.lo = __ldcg(ws.rlo + m.cw);
+        m.hi = __ldcg(ws.rhi + m.cw);
+    }
+    return m;
+}
+
 template <int S, int THREADS, int MINB, bool FAST>
 __global__ void __launch_bounds__(THREADS, MINB)
 eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
@@ -400,21 +560,35 @@ eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const do
     const int SP = Sx | 1;
     const int total = ws.counters[1];
     double* scratch = sm.scratch[warp];
-    const int gwarp = blockIdx.x * NWARP + warp, nwarps = gridDim.x * NWARP;
+    // stage 1 is complete: rearm its per-tile group queues for the next launch
+    for (int i = blockIdx.x * THREADS + threadIdx.x; i < ws.ntilectr; i += gridDim.x * THREADS) ws.tilectr[i] = 0;
 
-    for (int item = gwarp; item < total; item += nwarps) {
-        const int cw = __ldg(ws.itemwalker + item);
+    // dynamic item queue, software pipelined: the index two items ahead is being fetched and the
+    // metadata of the next item is in flight while the current item is evaluated
+    int* queue = ws.counters + 2;
+    int idx_cur = 0, idx_nxt = 0;
+    if (lane == 0) {
+        idx_cur = atomicAdd(queue, 1);
+        idx_nxt = atomicAdd(queue, 1);
+    }
+    idx_cur = __shfl_sync(0xffffffffu, idx_cur, 0);
+    idx_nxt = __shfl_sync(0xffffffffu, idx_nxt, 0);
+    ItemMeta nxt = load_item_meta(ws, idx_cur, total);
+    while (idx_cur < total) {
+        const int item = idx_cur;
+        const ItemMeta cur = nxt;
+        int idx_nn = 0;
+        if (lane == 0) idx_nn = atomicAdd(queue, 1);
+        nxt = load_item_meta(ws, idx_nxt, total);
+        const int cw = cur.cw;
         const int cand = cw / W;
-        const int first = __ldcg(ws.blkstart + cw);
-        const int nch = __ldcg(ws.blkstart + cw + 1) - first;
-        const int lo = __ldcg(ws.rlo + cw), hi = __ldcg(ws.rhi + cw);
         const WalkerConsts wc = ws.wcs[cw];
-        const int ci = item - first;
-        const int n_w = hi - lo;
-        int clen = (n_w + nch - 1) / nch;
+        const int ci = item - cur.first;
+        const int n_w = cur.hi - cur.lo;
+        int clen = (n_w + cur.nch - 1) / cur.nch;
         clen = (clen + TSW - 1) / TSW * TSW;
-        const int cstart = lo + ci * clen;
-        const int cend = min(hi, cstart + clen);
+        const int cstart = cur.lo + ci * clen;
+        const int cend = min(cur.hi, cstart + clen);
         const double* __restrict__ gt = lc.t + (long long)cand * lc.npad;
         const double* __restrict__ gf = lc.f + (long long)cand * lc.npad;
         const double* __restrict__ gw = lc.w + (long long)cand * lc.npad;
@@ -438,27 +612,34 @@ eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const do
             __syncwarp();
         }
         acc = warp_sum(acc);
-        int done = 0;
-        if (lane == 0) {
-            ws.itempart[item] = acc;
-            __threadfence();
-            done = atomicAdd(ws.itemsdone + cw, 1);
-        }
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done == nch - 1) {  // this warp completed the walker: fold its items, add the priors
-            __threadfence();
-            double s = 0.0;
-            for (int c = lane; c < nch; c += 32) s += __ldcg(ws.itempart + first + c);
-            s = warp_sum(s);
+        bool fold = (cur.nch == 1);
+        double s = acc;
+        if (!fold) {  // several items per walker: publish, and let the last one fold them in order
+            int done = 0;
             if (lane == 0) {
-                const double ll = ws.oot[cw] + s;
-                if (loglike) loglike[cw] = ll;
-                lnprob[cw] = ll + (priors ? ln_prior_dev(params + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0);
-                ws.itemsdone[cw] = 0;
-                ws.rlo[cw] = INT_MAX;
-                ws.rhi[cw] = 0;
+                ws.itempart[item] = acc;
+                __threadfence();
+                done = atomicAdd(ws.itemsdone + cw, 1);
+            }
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done == cur.nch - 1) {
+                __threadfence();
+                s = 0.0;
+                for (int c = lane; c < cur.nch; c += 32) s += __ldcg(ws.itempart + cur.first + c);
+                s = warp_sum(s);
+                fold = true;
             }
         }
+        if (fold && lane == 0) {
+            const double ll = ws.oot[cw] + s;
+            if (loglike) loglike[cw] = ll;
+            lnprob[cw] = ll + ws.lp[cw];
+            ws.itemsdone[cw] = 0;
+            ws.rlo[cw] = INT_MAX;
+            ws.rhi[cw] = 0;
+        }
+        idx_cur = idx_nxt;
+        idx_nxt = __shfl_sync(0xffffffffu, idx_nn, 0);
     }
 }
 

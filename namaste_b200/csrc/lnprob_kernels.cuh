@@ -15,6 +15,7 @@
 // Reference path: namaste/namaste.py:1155-1164 (get_value), :1347 (likelihood),
 // :1314-1332 (priors); namaste/Crossfield_transit.py:690-970 (occultquad).
 #pragma once
+#include <limits.h>
 #include <stdint.h>
 
 #include "transit_math.cuh"
@@ -29,6 +30,12 @@ struct LcView {
     const double* pre_lo;  // [C][npad+1] low word (double-double)
     const double* off;     // [C][S]      cad * (k * (1/S))        (namaste.py:1159)
     const long long* n;    // [C]
+    // uniform time grid for O(1) window lookup: tgrid[c][j] = #{i : t_i < t0[c] + j*gwidth[c]}
+    const int* tgrid;      // [C][gstride]
+    const double* t0;      // [C]
+    const double* ginv;    // [C]  1 / cell width
+    const int* gcount;     // [C]  last valid j
+    long long gstride;
     long long npad;
     int ncand;
     int S;
@@ -36,10 +43,30 @@ struct LcView {
 
 struct WalkerConsts {
     double tcen, vel, b2;
-    double qthr;  // conservative bound: fma(vx,vx,b2) > qthr  =>  sqrt(b2 + vx*vx) > 1 + p
-    double fbar;  // mean of S out-of-transit samples (== 1.0 unless the LD coefficients are inf/NaN)
+    double qthr;   // conservative bound: fma(vx,vx,b2) > qthr  =>  sqrt(b2 + vx*vx) > 1 + p   (vx faithful)
+    double fbar;   // mean of S out-of-transit samples (== 1.0 unless the LD coefficients are inf/NaN)
+    double nvtc;   // -(vel * tcen): vx' = fma(vel, ft, nvtc) is the 1-FMA position used by the sweep
+    double qthr_c; // conservative bound for q' = fma(vx', vx', b2), covers the cancellation error of vx'
+    int qhi;       // high word of qthr_c (INT_MAX if any sweep constant is not finite): a sample is a
+                   // candidate iff hi32(q') <= qhi, an integer compare that keeps the FP64 pipe for FMAs
+    int pad_;
     QuadConsts q;
 };
+
+// mean of S copies of x in NumPy's pairwise order (bin_mean of a constant bin)
+__device__ __forceinline__ double bin_mean_const(double x, int S) {
+    double res;
+    if (S < 8) {
+        res = 0.0;
+        for (int i = 0; i < S; ++i) res += x;
+    } else {
+        double r = x;
+        for (int i = 8; i < S - (S % 8); i += 8) r += x;
+        res = ((r + r) + (r + r)) + ((r + r) + (r + r));
+        for (int i = 0; i < S % 8; ++i) res += x;
+    }
+    return res / (double)S;
+}
 
 __device__ __forceinline__ WalkerConsts make_walker_consts(const double* par, int S) {
     WalkerConsts w;
@@ -50,9 +77,18 @@ __device__ __forceinline__ WalkerConsts make_walker_consts(const double* par, in
     finish_quad_consts(w.q);
     // rounding slack: q_fma and q_faithful differ by < 2 ulp, sqrt rounds by 1/2 ulp
     w.qthr = (w.q.p == 0.0) ? -1.0 : (w.q.onep * w.q.onep) * (1.0 + 16 * kEps);
-    double tmp[32];
-    for (int k = 0; k < S && k < 32; ++k) tmp[k] = w.q.fout;
-    w.fbar = bin_mean_rt(tmp, S < 32 ? S : 32);
+    w.fbar = (w.q.fout == 1.0) ? 1.0 : bin_mean_const(w.q.fout, S);
+    // one-FMA position vx' = vel*ft - vel*tcen: |vx' - vx| <= eps*|vel*tcen| + 3 eps |vx'|, hence
+    // q' > (eps|vtc| + sqrt(eps^2 vtc^2 + (1+p)^2))^2 (1 + O(eps))  =>  the faithful z exceeds 1+p
+    const double vtc = w.vel * w.tcen;
+    w.nvtc = -vtc;
+    const double ev = kEps * fabs(vtc);
+    const double u = (ev + ::sqrt(ev * ev + w.q.onep * w.q.onep)) * (1.0 + 32 * kEps);
+    w.qthr_c = (w.q.p == 0.0) ? -1.0 : u * u * (1.0 + 8 * kEps);
+    // q' >= 0 for finite inputs, so its IEEE bit pattern orders like an integer
+    const bool finite = (fabs(w.vel) <= 1e300) && (fabs(vtc) <= 1e300) && (w.b2 <= 1e300) && (w.qthr_c <= 1e300);
+    w.qhi = !finite ? INT_MAX : (w.qthr_c < 0.0 ? -1 : __double2hiint(w.qthr_c));
+    w.pad_ = 0;
     return w;
 }
 
