@@ -98,6 +98,33 @@ int nmb_occultquad(const double* z, int64_t n, double rprs, double ld1, double l
 /* lnprior [W] device out; params [W][npar] device; priors [npar][6] device */
 int nmb_lnprior(const double* params, int64_t W, int npar, const double* priors, double* lnprior, void* stream);
 
+/* ---- device-resident ensemble sampler (emcee 2.x stretch move, namaste/namaste.py:590-594) ----
+ * The ensemble, its log-probabilities, the chain [ncand][W][T][6] and lnprobability [ncand][W][T]
+ * live in HBM; a half-step is two kernel launches and no host round trip.  Random numbers are
+ * Philox4x32-10 keyed by `seed` with counter (step, half, candidate, walker): a chain does not
+ * depend on the launch geometry or on how walkers are split across GPUs. */
+int nmb_sampler_create(nmb_lc* lc, int64_t W, const double* priors /*host [ncand][6][6] or NULL*/, uint64_t seed,
+                       double a /*stretch scale, emcee default 2*/, int mode, nmb_sampler** out);
+void nmb_sampler_destroy(nmb_sampler* s);
+/* pos host [ncand][W][6]; lnp host [ncand][W] or NULL (then evaluated on the device).
+ * NMB_ERR_ARG for NaN/inf parameters, NMB_ERR_NAN if an initial lnprob is NaN (emcee: ValueError). */
+int nmb_sampler_set_state(nmb_sampler* s, const double* pos, const double* lnp);
+/* nsteps full steps (both half-ensembles); every thin-th step is appended when store != 0.
+ * Synchronises at the end; NMB_ERR_NAN if any lnprob evaluation returned NaN. */
+int nmb_sampler_run(nmb_sampler* s, int64_t nsteps, int64_t thin, int store);
+/* building blocks for the multi-GPU walker split: update walkers [k0, k0+nk) of one half ... */
+int nmb_sampler_halfstep(nmb_sampler* s, int half, int64_t k0, int64_t nk, int store);
+/* ... then close the step (RNG counter, chain column; append_all appends the whole ensemble) */
+int nmb_sampler_advance(nmb_sampler* s, int stored, int append_all);
+int nmb_sampler_sync(nmb_sampler* s);
+int nmb_sampler_reset(nmb_sampler* s);
+int64_t nmb_sampler_len(const nmb_sampler* s);   /* stored chain columns */
+int64_t nmb_sampler_steps(const nmb_sampler* s); /* steps taken (RNG counter) */
+/* what: 0 pos, 1 lnp, 2 chain [ncand][W][len][6], 3 lnprobability [ncand][W][len], 4 naccepted (int64) */
+int nmb_sampler_get(nmb_sampler* s, int what, void* out);
+void* nmb_sampler_devptr(nmb_sampler* s, int what /*0 pos, 1 lnp*/);
+void* nmb_sampler_stream(nmb_sampler* s);
+
 /* ---- measurement helpers (used by bench.py) ------------------------------------------------ */
 /* Sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), CUDA-event timed. */
 int nmb_measure_fp64_peak(double* tflops, double* ms);

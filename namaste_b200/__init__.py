@@ -7,6 +7,7 @@ CUDA library (namaste_b200/csrc, C ABI in include/namaste_b200.h); there is no C
 """
 from .namaste import (MonotransitModel, MonoLnPrior, MonoOnlyLogProb, MonoOnlyNegLogProb, CalcTdur, CalcVel,
                       stage_lightcurve, clear_cache)
+from .sampler import EnsembleSampler
 from .core import LightCurve, occultquad, lnprior, prior_table, measure_fp64_peak, launch_count, PARAM_NAMES
 
 __version__ = "0.1.0"

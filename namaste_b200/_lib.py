@@ -37,6 +37,20 @@ SIGNATURES = {
     "nmb_occultquad": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp,
                                       _vp]),
     "nmb_lnprior": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
+    "nmb_sampler_create": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_uint64, ctypes.c_double, ctypes.c_int,
+                                          ctypes.POINTER(_vp)]),
+    "nmb_sampler_destroy": (None, [_vp]),
+    "nmb_sampler_set_state": (ctypes.c_int, [_vp, _vp, _vp]),
+    "nmb_sampler_run": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    "nmb_sampler_halfstep": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    "nmb_sampler_advance": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "nmb_sampler_sync": (ctypes.c_int, [_vp]),
+    "nmb_sampler_reset": (ctypes.c_int, [_vp]),
+    "nmb_sampler_len": (ctypes.c_int64, [_vp]),
+    "nmb_sampler_steps": (ctypes.c_int64, [_vp]),
+    "nmb_sampler_get": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "nmb_sampler_devptr": (_vp, [_vp, ctypes.c_int]),
+    "nmb_sampler_stream": (_vp, [_vp]),
     "nmb_measure_fp64_peak": (ctypes.c_int, [_c_double_p, _c_double_p]),
     "nmb_launch_count": (ctypes.c_int64, []),
 }

@@ -333,7 +333,7 @@ EvalShape eval_shape(int S, size_t CW) {
 
 template <int S, int MINB>
 int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                   cudaStream_t st) {
+                   cudaStream_t st, const nmb::SampleCtx& sc) {
     auto kern = nmb::eval_ranges_kernel<S, kEvalThreads, MINB, true>;
     const size_t smem = sizeof(nmb::EvalSmem<S, kEvalThreads>);
     static thread_local int grid = 0;
@@ -346,7 +346,7 @@ int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors
         grid = sms * std::max(per_sm, 1);
     }
     kern<<<grid, kEvalThreads, smem, st>>>(lc->view(), params, W, priors, lc->ws,
-                                           eval_shape(lc->S, (size_t)lc->ncand * W).tsw, lnprob, loglike);
+                                           eval_shape(lc->S, (size_t)lc->ncand * W).tsw, lnprob, loglike, sc);
     g_launches++;
     CU(cudaGetLastError());
     return NMB_OK;
@@ -354,17 +354,17 @@ int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors
 
 template <int S>
 int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                cudaStream_t st) {
+                cudaStream_t st, const nmb::SampleCtx& sc) {
     static const int mb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 4;
-    if (mb == 6) return launch_eval_mb<S, 6>(lc, params, W, priors, lnprob, loglike, st);
-    if (mb == 5) return launch_eval_mb<S, 5>(lc, params, W, priors, lnprob, loglike, st);
-    if (mb == 3) return launch_eval_mb<S, 3>(lc, params, W, priors, lnprob, loglike, st);
-    return launch_eval_mb<S, 4>(lc, params, W, priors, lnprob, loglike, st);
+    if (mb == 6) return launch_eval_mb<S, 6>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (mb == 5) return launch_eval_mb<S, 5>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (mb == 3) return launch_eval_mb<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+    return launch_eval_mb<S, 4>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
 
 template <int S>
 int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                 cudaStream_t st) {
+                 cudaStream_t st, const nmb::SampleCtx& sc) {
     constexpr int WT = 8, MINB = 4;
     constexpr int kBlock = kThreads + 32;  // 4 consumer warps + 1 producer warp
     const int ntiles = (int)(lc->npad / kTile);
@@ -388,14 +388,14 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     const int by = (int)std::min<long long>(groups, per_tile);
     dim3 grid(ntiles, by, (unsigned)lc->ncand);
     g_timer.mark(0, st);
-    nmb::walker_setup_kernel<<<(unsigned)((CW + 63) / 64), 64, 0, st>>>(lc->view(), params, W, priors, lc->ws);
+    nmb::walker_setup_kernel<<<(unsigned)((CW + 63) / 64), 64, 0, st>>>(lc->view(), params, W, priors, lc->ws, sc);
     g_launches++;
     kern<<<grid, kBlock, smem, st>>>(lc->view(), params, W, groups, priors, lc->ws,
-                                       eval_shape(lc->S, CW).item_ts, lnprob, loglike);
+                                       eval_shape(lc->S, CW).item_ts, lnprob, loglike, sc);
     g_launches++;
     CU(cudaGetLastError());
     g_timer.mark(1, st);
-    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc);
     g_timer.mark(2, st);
     g_timer.done("brute");
     return rc;
@@ -403,17 +403,17 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
 
 template <int S>
 int launch_window(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                  cudaStream_t st) {
+                  cudaStream_t st, const nmb::SampleCtx& sc) {
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
     constexpr int kWinThreads = 64;
     g_timer.mark(0, st);
     nmb::window_ranges_kernel<kWinThreads><<<(unsigned)((CW + kWinThreads - 1) / kWinThreads), kWinThreads, 0, st>>>(
-        lc->view(), params, W, priors, lc->ws, eval_shape(lc->S, (size_t)lc->ncand * W).item_ts, lnprob, loglike);
+        lc->view(), params, W, priors, lc->ws, eval_shape(lc->S, (size_t)lc->ncand * W).item_ts, lnprob, loglike, sc);
     g_launches++;
     CU(cudaGetLastError());
     g_timer.mark(1, st);
-    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st);
+    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc);
     g_timer.mark(2, st);
     g_timer.done("windowed");
     return rc;
@@ -478,23 +478,29 @@ int launch_model(nmb_lc* lc, int cand, const double* params, int W, double* mode
 
 }  // namespace
 
-extern "C" int nmb_lnprob(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
-                          double* loglike, int mode, int dtype, void* stream) {
-    if (!lc || !params || !lnprob) return fail(NMB_ERR_ARG, "nmb_lnprob: null pointer");
+static int lnprob_impl(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
+                       double* loglike, int mode, int dtype, void* stream, const nmb::SampleCtx& sc) {
+    if (!lc || !params || (!lnprob && !sc.enabled)) return fail(NMB_ERR_ARG, "nmb_lnprob: null pointer");
     if (W < 1 || W > (1 << 24)) return fail(NMB_ERR_ARG, "nmb_lnprob: W out of range");
     if (dtype != NMB_F64) return fail(NMB_ERR_ARG, "nmb_lnprob: only NMB_F64 is implemented in this build");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = NMB_OK;
     if (mode == NMB_MODE_BRUTE) {
-        NMB_DISPATCH_S(lc->S, rc = launch_sweep<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
+        NMB_DISPATCH_S(lc->S, rc = launch_sweep<SS>(lc, params, (int)W, priors, lnprob, loglike, st, sc));
     } else if (mode == NMB_MODE_WINDOWED) {
-        NMB_DISPATCH_S(lc->S, rc = launch_window<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
+        NMB_DISPATCH_S(lc->S, rc = launch_window<SS>(lc, params, (int)W, priors, lnprob, loglike, st, sc));
     } else if (mode == NMB_MODE_FUSED) {
         NMB_DISPATCH_S(lc->S, rc = launch_fused<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
     } else {
         return fail(NMB_ERR_ARG, "nmb_lnprob: unknown mode");
     }
     return rc;
+}
+
+extern "C" int nmb_lnprob(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
+                          double* loglike, int mode, int dtype, void* stream) {
+    nmb::SampleCtx sc{};
+    return lnprob_impl(lc, params, W, priors, lnprob, loglike, mode, dtype, stream, sc);
 }
 
 extern "C" int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
@@ -587,3 +593,232 @@ extern "C" int nmb_measure_fp64_peak(double* tflops, double* ms_out) {
     cudaFree(d);
     return NMB_OK;
 }
+
+// =============================================================================================
+// Device-resident ensemble sampler (stretch move); see sampler.cuh
+// =============================================================================================
+struct nmb_sampler {
+    nmb_lc* lc = nullptr;
+    int64_t W = 0, C = 0;
+    int mode = NMB_MODE_WINDOWED;
+    double a = 2.0;
+    unsigned long long seed = 0;
+    double *d_pos = nullptr, *d_lnp = nullptr, *d_q = nullptr, *d_zz = nullptr, *d_logu = nullptr;
+    double *d_chain = nullptr, *d_lnpchain = nullptr, *d_priors = nullptr;
+    long long* d_nacc = nullptr;
+    int* d_nan = nullptr;
+    int64_t tcap = 0, tlen = 0;
+    long long step = 0;
+    bool has_state = false;
+    cudaStream_t st = nullptr;
+};
+
+namespace {
+
+__global__ void append_chain_kernel(nmb::SampleCtx sc, long long n) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    double* row = sc.chain + (g * sc.tcap + sc.tcol) * sc.ndim;
+    for (int d = 0; d < sc.ndim; ++d) row[d] = sc.pos[g * sc.ndim + d];
+    sc.lnpchain[g * sc.tcap + sc.tcol] = sc.lnp[g];
+}
+
+int sampler_reserve(nmb_sampler* s, int64_t need) {
+    if (need <= s->tcap) return NMB_OK;
+    int64_t cap = std::max<int64_t>(need, std::max<int64_t>(16, s->tcap * 2));
+    const size_t rows = (size_t)s->C * s->W;
+    double *nc = nullptr, *nl = nullptr;
+    CU(cudaMalloc(&nc, rows * cap * 6 * sizeof(double)));
+    CU(cudaMalloc(&nl, rows * cap * sizeof(double)));
+    if (s->tlen > 0) {
+        CU(cudaMemcpy2DAsync(nc, cap * 48, s->d_chain, s->tcap * 48, s->tlen * 48, rows, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaMemcpy2DAsync(nl, cap * 8, s->d_lnpchain, s->tcap * 8, s->tlen * 8, rows, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));
+    }
+    cudaFree(s->d_chain);
+    cudaFree(s->d_lnpchain);
+    s->d_chain = nc;
+    s->d_lnpchain = nl;
+    s->tcap = cap;
+    return NMB_OK;
+}
+
+nmb::SampleCtx sampler_ctx(nmb_sampler* s, int half, int k0, int store) {
+    nmb::SampleCtx sc{};
+    sc.enabled = 1; sc.W = (int)s->W; sc.half = half; sc.k0 = k0; sc.store = store; sc.ndim = 6;
+    sc.step = s->step; sc.tcol = s->tlen; sc.tcap = s->tcap; sc.seed = s->seed; sc.a = s->a;
+    sc.pos = s->d_pos; sc.lnp = s->d_lnp; sc.q = s->d_q; sc.zz = s->d_zz; sc.logu = s->d_logu;
+    sc.chain = s->d_chain; sc.lnpchain = s->d_lnpchain; sc.nacc = s->d_nacc; sc.nan_count = s->d_nan;
+    return sc;
+}
+
+int sampler_check_nan(nmb_sampler* s, const char* what) {
+    int nan = 0;
+    CU(cudaMemcpyAsync(&nan, s->d_nan, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    if (nan) {
+        CU(cudaMemsetAsync(s->d_nan, 0, sizeof(int), s->st));
+        return fail(NMB_ERR_NAN, what);
+    }
+    return NMB_OK;
+}
+
+}  // namespace
+
+extern "C" void nmb_sampler_destroy(nmb_sampler* s) {
+    if (!s) return;
+    cudaFree(s->d_pos); cudaFree(s->d_lnp); cudaFree(s->d_q); cudaFree(s->d_zz); cudaFree(s->d_logu);
+    cudaFree(s->d_chain); cudaFree(s->d_lnpchain); cudaFree(s->d_priors); cudaFree(s->d_nacc); cudaFree(s->d_nan);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+}
+
+extern "C" int nmb_sampler_create(nmb_lc* lc, int64_t W, const double* priors, uint64_t seed, double a, int mode,
+                                  nmb_sampler** out) {
+    if (!lc || !out) return fail(NMB_ERR_ARG, "nmb_sampler_create: null pointer");
+    if (W < 2 || (W % 2) != 0) return fail(NMB_ERR_ARG, "The number of walkers must be even.");
+    if (W < 2 * NMB_NPAR)
+        return fail(NMB_ERR_ARG, "The number of walkers needs to be more than twice the dimension of your parameter space.");
+    if (!(a > 1.0)) return fail(NMB_ERR_ARG, "nmb_sampler_create: stretch scale a must be > 1");
+    if (mode != NMB_MODE_BRUTE && mode != NMB_MODE_WINDOWED) return fail(NMB_ERR_ARG, "nmb_sampler_create: unknown mode");
+    nmb_sampler* s = new nmb_sampler;
+    s->lc = lc; s->W = W; s->C = lc->ncand; s->mode = mode; s->a = a; s->seed = seed;
+    const size_t rows = (size_t)s->C * W, hrows = (size_t)s->C * (W / 2);
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&s->d_pos, rows * 6 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_lnp, rows * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_q, hrows * 6 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_zz, hrows * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_logu, hrows * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_nacc, rows * sizeof(long long))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_nan, sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(s->d_nacc, 0, rows * sizeof(long long))) != cudaSuccess ||
+        (e = cudaMemset(s->d_nan, 0, sizeof(int))) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)) != cudaSuccess) {
+        nmb_sampler_destroy(s);
+        return cuda_fail(e, "nmb_sampler_create");
+    }
+    if (priors) {
+        if ((e = cudaMalloc(&s->d_priors, (size_t)s->C * 36 * sizeof(double))) != cudaSuccess ||
+            (e = cudaMemcpy(s->d_priors, priors, (size_t)s->C * 36 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            nmb_sampler_destroy(s);
+            return cuda_fail(e, "nmb_sampler_create: priors");
+        }
+    }
+    *out = s;
+    return NMB_OK;
+}
+
+extern "C" int nmb_sampler_set_state(nmb_sampler* s, const double* pos, const double* lnp) {
+    if (!s || !pos) return fail(NMB_ERR_ARG, "nmb_sampler_set_state: null pointer");
+    const size_t rows = (size_t)s->C * s->W;
+    for (size_t i = 0; i < rows * 6; ++i)
+        if (!std::isfinite(pos[i])) return fail(NMB_ERR_ARG, std::isnan(pos[i]) ? "At least one parameter value was NaN."
+                                                                                : "At least one parameter value was infinite.");
+    CU(cudaMemcpyAsync(s->d_pos, pos, rows * 6 * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    if (lnp) {
+        CU(cudaMemcpyAsync(s->d_lnp, lnp, rows * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    } else {
+        nmb::SampleCtx off{};
+        if (int rc = lnprob_impl(s->lc, s->d_pos, s->W, s->d_priors, s->d_lnp, nullptr, s->mode, NMB_F64, s->st, off)) return rc;
+    }
+    std::vector<double> h(rows);
+    CU(cudaMemcpyAsync(h.data(), s->d_lnp, rows * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    for (double v : h)
+        if (std::isnan(v)) return fail(NMB_ERR_NAN, "The initial lnprob was NaN.");
+    s->has_state = true;
+    return NMB_OK;
+}
+
+// One half-step for walkers [k0, k0+nk) of half `half` (the whole half when nk == W/2).
+extern "C" int nmb_sampler_halfstep(nmb_sampler* s, int half, int64_t k0, int64_t nk, int store) {
+    if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_halfstep: null pointer");
+    if (!s->has_state) return fail(NMB_ERR_ARG, "nmb_sampler_halfstep: no state (call set_state first)");
+    if (half < 0 || half > 1 || k0 < 0 || nk < 1 || k0 + nk > s->W / 2) return fail(NMB_ERR_ARG, "nmb_sampler_halfstep: bad slice");
+    if (store)
+        if (int rc = sampler_reserve(s, s->tlen + 1)) return rc;
+    const nmb::SampleCtx sc = sampler_ctx(s, half, (int)k0, store);
+    return lnprob_impl(s->lc, s->d_q, nk, s->d_priors, nullptr, nullptr, s->mode, NMB_F64, s->st, sc);
+}
+
+// Close a step driven through nmb_sampler_halfstep: advance the RNG step, count a stored column.
+extern "C" int nmb_sampler_advance(nmb_sampler* s, int stored, int append_all) {
+    if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_advance: null pointer");
+    if (append_all) {  // (multi-GPU walker split) append the gathered ensemble as one chain column
+        if (int rc = sampler_reserve(s, s->tlen + 1)) return rc;
+        const nmb::SampleCtx sc = sampler_ctx(s, 0, 0, 1);
+        const long long n = (long long)s->C * s->W;
+        append_chain_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->st>>>(sc, n);
+        g_launches++;
+        CU(cudaGetLastError());
+        stored = 1;
+    }
+    s->step += 1;
+    if (stored) s->tlen += 1;
+    return NMB_OK;
+}
+
+extern "C" int nmb_sampler_run(nmb_sampler* s, int64_t nsteps, int64_t thin, int store) {
+    if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_run: null pointer");
+    if (!s->has_state) return fail(NMB_ERR_ARG, "Cannot have pos0=None if run_mcmc has never been called.");
+    if (nsteps < 0 || thin < 1) return fail(NMB_ERR_ARG, "nmb_sampler_run: bad nsteps/thin");
+    if (store)
+        if (int rc = sampler_reserve(s, s->tlen + nsteps / thin + 1)) return rc;
+    const int64_t halfk = s->W / 2;
+    for (int64_t i = 0; i < nsteps; ++i) {
+        const int st_col = (store && (i % thin == 0)) ? 1 : 0;
+        for (int half = 0; half < 2; ++half) {
+            const nmb::SampleCtx sc = sampler_ctx(s, half, 0, st_col);
+            if (int rc = lnprob_impl(s->lc, s->d_q, halfk, s->d_priors, nullptr, nullptr, s->mode, NMB_F64, s->st, sc))
+                return rc;
+        }
+        s->step += 1;
+        if (st_col) s->tlen += 1;
+    }
+    return sampler_check_nan(s, "lnprob returned NaN.");
+}
+
+extern "C" int nmb_sampler_sync(nmb_sampler* s) {
+    if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_sync: null pointer");
+    return sampler_check_nan(s, "lnprob returned NaN.");
+}
+
+extern "C" int64_t nmb_sampler_len(const nmb_sampler* s) { return s ? s->tlen : -1; }
+extern "C" int64_t nmb_sampler_steps(const nmb_sampler* s) { return s ? s->step : -1; }
+
+extern "C" int nmb_sampler_reset(nmb_sampler* s) {
+    if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_reset: null pointer");
+    s->tlen = 0;
+    CU(cudaMemsetAsync(s->d_nacc, 0, (size_t)s->C * s->W * sizeof(long long), s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return NMB_OK;
+}
+
+// what: 0 pos [C][W][6], 1 lnp [C][W], 2 chain [C][W][len][6], 3 lnprobability [C][W][len], 4 naccepted (int64) [C][W]
+extern "C" int nmb_sampler_get(nmb_sampler* s, int what, void* out) {
+    if (!s || !out) return fail(NMB_ERR_ARG, "nmb_sampler_get: null pointer");
+    const size_t rows = (size_t)s->C * s->W;
+    switch (what) {
+        case 0: CU(cudaMemcpyAsync(out, s->d_pos, rows * 48, cudaMemcpyDeviceToHost, s->st)); break;
+        case 1: CU(cudaMemcpyAsync(out, s->d_lnp, rows * 8, cudaMemcpyDeviceToHost, s->st)); break;
+        case 2:
+            if (s->tlen) CU(cudaMemcpy2DAsync(out, s->tlen * 48, s->d_chain, s->tcap * 48, s->tlen * 48, rows, cudaMemcpyDeviceToHost, s->st));
+            break;
+        case 3:
+            if (s->tlen) CU(cudaMemcpy2DAsync(out, s->tlen * 8, s->d_lnpchain, s->tcap * 8, s->tlen * 8, rows, cudaMemcpyDeviceToHost, s->st));
+            break;
+        case 4: CU(cudaMemcpyAsync(out, s->d_nacc, rows * 8, cudaMemcpyDeviceToHost, s->st)); break;
+        default: return fail(NMB_ERR_ARG, "nmb_sampler_get: unknown item");
+    }
+    CU(cudaStreamSynchronize(s->st));
+    return NMB_OK;
+}
+
+// device pointers for zero-copy interop (torch.distributed all-gather of the walker-split mode):
+// what: 0 pos, 1 lnp.  The stream is the sampler's own; use nmb_sampler_stream to order against it.
+extern "C" void* nmb_sampler_devptr(nmb_sampler* s, int what) {
+    if (!s) return nullptr;
+    return what == 0 ? (void*)s->d_pos : what == 1 ? (void*)s->d_lnp : nullptr;
+}
+extern "C" void* nmb_sampler_stream(nmb_sampler* s) { return s ? (void*)s->st : nullptr; }

@@ -25,6 +25,7 @@
 #include <limits.h>
 
 #include "lnprob_kernels.cuh"
+#include "sampler.cuh"
 
 namespace nmb {
 
@@ -46,6 +47,15 @@ struct EvalWs {
     int ntilectr;
     int maxch;
 };
+
+// Every evaluated walker ends here exactly once: plain evaluation writes the outputs, sampler mode
+// runs the accept/reject step of the stretch move instead.
+__device__ __forceinline__ void finish_walker(const SampleCtx& sc, long long cw, int W, double ll, double lp,
+                                              double* __restrict__ lnprob, double* __restrict__ loglike) {
+    if (loglike) loglike[cw] = ll;
+    if (lnprob) lnprob[cw] = ll + lp;
+    if (sc.enabled) accept_stretch(sc, (int)(cw / W), (int)(cw % W), W, ll + lp);
+}
 
 template <int S>
 __host__ __device__ constexpr int ts_per_block(int threads, int s_rt) {
@@ -148,7 +158,7 @@ template <int S, int CTHREADS, int TPT, int WT, int MINB>
 __global__ void __launch_bounds__(CTHREADS + 32, MINB)
 sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int ngroups,
                       const double* __restrict__ priors, EvalWs ws, int item_ts, double* __restrict__ lnprob,
-                      double* __restrict__ loglike) {
+                      double* __restrict__ loglike, SampleCtx sc) {
     constexpr int TT = CTHREADS * TPT;
     constexpr int NCW = CTHREADS / 32;  // consumer warps
     constexpr int ALL = CTHREADS + 32;
@@ -215,8 +225,7 @@ sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int n
                         for (int i = 0; i < ntiles; ++i) sacc += __ldcg(row + i);
                         const int n_w = __ldcg(ws.rhi + cw) - __ldcg(ws.rlo + cw);
                         if (n_w <= 0) {  // never in transit: done here
-                            if (loglike) loglike[cw] = sacc;
-                            lnprob[cw] = sacc + ws.lp[cw];
+                            finish_walker(sc, cw, W, sacc, ws.lp[cw], lnprob, loglike);
                             ws.rlo[cw] = INT_MAX;
                             ws.rhi[cw] = 0;
                         } else {
@@ -289,8 +298,7 @@ sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int n
                             for (int i = 0; i < ntiles; ++i) sacc += __ldcg(row + i);
                             const int n_w = __ldcg(ws.rhi + cw) - __ldcg(ws.rlo + cw);
                             if (n_w <= 0) {
-                                if (loglike) loglike[cw] = sacc;
-                                lnprob[cw] = sacc + ws.lp[cw];
+                                finish_walker(sc, cw, W, sacc, ws.lp[cw], lnprob, loglike);
                                 ws.rlo[cw] = INT_MAX;
                                 ws.rhi[cw] = 0;
                             } else {
@@ -385,12 +393,17 @@ sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int n
 
 // ---- per-walker setup for the brute-force sweep: constants + log-prior, one thread per walker ----
 __global__ void walker_setup_kernel(LcView lc, const double* __restrict__ params, int W,
-                                    const double* __restrict__ priors, EvalWs ws) {
+                                    const double* __restrict__ priors, EvalWs ws, SampleCtx sc) {
     const int cw = blockIdx.x * blockDim.x + threadIdx.x;
     if (cw >= W * lc.ncand) return;
     const int cand = cw / W;
-    ws.wcs[cw] = make_walker_consts(params + (long long)cw * 6, lc.S);
-    ws.lp[cw] = priors ? ln_prior_dev(params + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
+    const double* par = params;
+    if (sc.enabled) {
+        propose_stretch(sc, cand, cw % W, W);
+        par = sc.q;  // the proposal just written by this thread (not through the read-only path)
+    }
+    ws.wcs[cw] = make_walker_consts(par + (long long)cw * 6, lc.S);
+    ws.lp[cw] = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
 }
 
 // ---- windowed stage 1: one thread per walker ---------------------------------------------------
@@ -409,7 +422,8 @@ __device__ __forceinline__ int bsearch_t(const double* __restrict__ t, int n, do
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors,
-                     EvalWs ws, int item_ts, double* __restrict__ lnprob, double* __restrict__ loglike) {
+                     EvalWs ws, int item_ts, double* __restrict__ lnprob, double* __restrict__ loglike,
+                     SampleCtx sc) {
     __shared__ int s_scan[THREADS / 32 + 1];
     __shared__ int s_last;
     const int tid = threadIdx.x;
@@ -419,7 +433,12 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
     if (cw < CW) {
         const int cand = cw / W;
         const int n = (int)lc.n[cand];
-        const WalkerConsts wc = make_walker_consts(params + (long long)cw * 6, Sx);
+        const double* par = params;
+        if (sc.enabled) {
+            propose_stretch(sc, cand, cw % W, W);
+            par = sc.q;  // the proposal just written by this thread (not through the read-only path)
+        }
+        const WalkerConsts wc = make_walker_consts(par + (long long)cw * 6, Sx);
         const double span = lc.off[(long long)cand * Sx + Sx - 1];
         const double hx2 = wc.qthr - wc.b2;
         bool full = !(wc.fbar == 1.0);  // prefix sums assume the out-of-transit model is exactly 1
@@ -464,10 +483,9 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
         two_sum(sa, ph[ilo], sb, eb);
         eb += ea + pl[ilo];
         const double oot = sb + eb;
-        const double lp = priors ? ln_prior_dev(params + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
+        const double lp = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
         if (ihi - ilo <= 0) {
-            if (loglike) loglike[cw] = oot;
-            lnprob[cw] = oot + lp;
+            finish_walker(sc, cw, W, oot, lp, lnprob, loglike);
             ws.rlo[cw] = INT_MAX;
             ws.rhi[cw] = 0;
         } else {
@@ -551,7 +569,7 @@ __device__ __forceinline__ ItemMeta load_item_meta(const EvalWs& ws, int item, i
 template <int S, int THREADS, int MINB, bool FAST>
 __global__ void __launch_bounds__(THREADS, MINB)
 eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
-                   int TSW, double* __restrict__ lnprob, double* __restrict__ loglike) {
+                   int TSW, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
     constexpr int NWARP = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EvalSmem<S, THREADS>& sm = *reinterpret_cast<EvalSmem<S, THREADS>*>(smem_raw);
@@ -631,9 +649,7 @@ eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const do
             }
         }
         if (fold && lane == 0) {
-            const double ll = ws.oot[cw] + s;
-            if (loglike) loglike[cw] = ll;
-            lnprob[cw] = ll + ws.lp[cw];
+            finish_walker(sc, cw, W, ws.oot[cw] + s, ws.lp[cw], lnprob, loglike);
             ws.itemsdone[cw] = 0;
             ws.rlo[cw] = INT_MAX;
             ws.rhi[cw] = 0;

@@ -1,0 +1,163 @@
+"""emcee-2.x-shaped front end of the device-resident ensemble sampler.
+
+Mirrors the surface Namaste uses (namaste/namaste.py:583-608; Example.ipynb cells 30-35):
+``EnsembleSampler(nwalkers, dim, lnpostfn, args=(), threads=1)``, ``run_mcmc(pos0, N, rstate0=None)``
+(successive calls append), ``.chain [W, T, dim]``, ``.lnprobability [W, T]``, ``.flatchain``,
+``.flatlnprobability``, ``.acceptance_fraction``, ``.naccepted``, ``.iterations``, ``.reset()``.
+
+``lnpostfn`` must be this package's ``MonoOnlyLogProb``: proposal, likelihood and accept/reject then
+run on the GPU with no per-step host round trip.  Any other callable raises ``TypeError`` (there is
+no CPU fallback).  Random numbers are Philox4x32-10 (counter based), not NumPy's Mersenne Twister:
+chains agree with emcee's in distribution, not draw by draw; ``rstate0`` only seeds the stream.
+"""
+import ctypes
+
+import numpy as np
+
+from . import core, namaste as _nm
+from ._lib import MODES, check, load, ptr, as_f64
+
+__all__ = ["EnsembleSampler"]
+
+
+def _seed_from(rstate0, seed):
+    if seed is not None:
+        return int(seed) & 0xFFFFFFFFFFFFFFFF
+    if rstate0 is None:
+        return int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+    if isinstance(rstate0, (int, np.integer)):
+        return int(rstate0) & 0xFFFFFFFFFFFFFFFF
+    try:  # np.random.get_state() tuple: fold the key words into 64 bits
+        key = np.asarray(rstate0[1], dtype=np.uint64)
+        h = np.uint64(1469598103934665603)
+        for w in key[:16]:
+            h = np.uint64((int(h) ^ int(w)) * 1099511628211 & 0xFFFFFFFFFFFFFFFF)
+        return int(h) ^ int(rstate0[2])
+    except Exception:
+        raise ValueError("rstate0 must be None, an integer seed or a numpy.random.get_state() tuple")
+
+
+class EnsembleSampler(object):
+    def __init__(self, nwalkers, dim, lnpostfn, a=2.0, args=(), kwargs=None, threads=1, pool=None,
+                 live_dangerously=False, mode="windowed", seed=None):
+        if lnpostfn not in (_nm.MonoOnlyLogProb,):
+            raise TypeError("namaste_b200.EnsembleSampler runs the log-probability on the GPU and only accepts "
+                            "namaste_b200.MonoOnlyLogProb as lnpostfn (no CPU fallback)")
+        if dim != 6:
+            raise ValueError("MonoOnlyLogProb has 6 parameters (tcen, b, vel, RpRs, LD1, LD2); got dim=%r" % (dim,))
+        if nwalkers % 2 != 0:
+            raise AssertionError("The number of walkers must be even.")
+        if nwalkers < 2 * dim:
+            raise AssertionError("The number of walkers needs to be more than twice the dimension of your "
+                                 "parameter space.")
+        if len(args) < 2:
+            raise ValueError("args must be (lc, priors[, monomodel]) as in namaste.py:590")
+        self.k, self.dim, self.a = int(nwalkers), int(dim), float(a)
+        self.args, self.threads = args, threads  # threads is accepted and ignored (one GPU does the work)
+        lc, priors = args[0], args[1]
+        model = args[2] if len(args) > 2 else None
+        self._oversamp = getattr(model, "oversamp", 10) if model is not None else 10
+        self._lc = lc if isinstance(lc, core.LightCurve) else _nm.stage_lightcurve(lc, self._oversamp)
+        self._ptab = core.prior_table(priors)
+        self._mode, self._seed0 = mode, seed
+        self._h = None
+        self._have_state = False
+        self.iterations = 0
+        self._last = None
+
+    # ---- handle management --------------------------------------------------------------------
+    def _ensure(self, rstate0):
+        if self._h is not None:
+            return
+        lib = load()
+        tab = None
+        if self._ptab is not None:
+            tab = np.ascontiguousarray(np.broadcast_to(self._ptab, (self._lc.ncand, 6, 6)))
+        h = ctypes.c_void_p()
+        check(lib.nmb_sampler_create(self._lc._h, self.k, ptr(tab), ctypes.c_uint64(_seed_from(rstate0, self._seed0)),
+                                     self.a, MODES[self._mode], ctypes.byref(h)), "EnsembleSampler")
+        self._h = h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                load().nmb_sampler_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- emcee surface ---------------------------------------------------------------------------
+    def run_mcmc(self, pos0, N, rstate0=None, lnprob0=None, thin=1, storechain=True, **kwargs):
+        """Advance the ensemble N steps from pos0 (or from where the last call stopped if None).
+        Returns (pos, lnprob, rstate) like emcee 2.x; rstate is the (seed, step) pair of the stream."""
+        lib = load()
+        self._ensure(rstate0)
+        if pos0 is None:
+            if not self._have_state:
+                raise ValueError("Cannot have pos0=None if run_mcmc has never been called.")
+        else:
+            p = as_f64(pos0)
+            want = (self.k, self.dim) if self._lc.ncand == 1 else (self._lc.ncand, self.k, self.dim)
+            if p.shape != want:
+                raise ValueError("pos0 must have shape %r" % (want,))
+            l0 = None if lnprob0 is None else as_f64(lnprob0)
+            check(lib.nmb_sampler_set_state(self._h, ptr(p), ptr(l0)), "run_mcmc")
+            self._have_state = True
+        check(lib.nmb_sampler_run(self._h, int(N), int(thin), 1 if storechain else 0), "run_mcmc")
+        self.iterations += int(N)
+        pos, lnp = self._get(0), self._get(1)
+        self._last = (pos, lnp)
+        return pos, lnp, ("philox4x32-10", int(lib.nmb_sampler_steps(self._h)))
+
+    def sample(self, p0, lnprob0=None, rstate0=None, iterations=1, thin=1, storechain=True, **kwargs):
+        """Generator form: yields (pos, lnprob, rstate) after every step."""
+        first = True
+        for _ in range(int(iterations)):
+            yield self.run_mcmc(p0 if first else None, 1, rstate0=rstate0, lnprob0=lnprob0 if first else None,
+                                thin=1, storechain=storechain)
+            first = False
+
+    def _get(self, what):
+        lib = load()
+        C, W = self._lc.ncand, self.k
+        T = int(lib.nmb_sampler_len(self._h)) if self._h is not None else 0
+        shape = {0: (C, W, 6), 1: (C, W), 2: (C, W, T, 6), 3: (C, W, T), 4: (C, W)}[what]
+        out = np.zeros(shape, dtype=np.int64 if what == 4 else np.float64)
+        if self._h is not None and out.size:
+            check(lib.nmb_sampler_get(self._h, what, ptr(out)), "EnsembleSampler")
+        return out[0] if C == 1 else out
+
+    @property
+    def chain(self):
+        """Markov chain, shape [nwalkers, iterations, dim] (emcee layout)."""
+        return self._get(2)
+
+    @property
+    def lnprobability(self):
+        return self._get(3)
+
+    @property
+    def flatchain(self):
+        c = self.chain
+        return c.reshape(c.shape[:-3] + (c.shape[-3] * c.shape[-2], self.dim))
+
+    @property
+    def flatlnprobability(self):
+        l = self.lnprobability
+        return l.reshape(l.shape[:-2] + (l.shape[-2] * l.shape[-1],))
+
+    @property
+    def naccepted(self):
+        return self._get(4)
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / float(max(self.iterations, 1))
+
+    def reset(self):
+        """Clear chain, lnprobability and acceptance counters (emcee: clear_chain/reset)."""
+        if self._h is not None:
+            check(load().nmb_sampler_reset(self._h), "reset")
+        self.iterations = 0
+
+    clear_chain = reset

@@ -1,0 +1,102 @@
+"""Device ensemble sampler vs the CPU stretch-move oracle (same Philox stream, NumPy likelihood)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, priors_from_table
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import torch
+    assert torch.cuda.is_available()
+    import namaste_b200
+    return namaste_b200
+
+
+def _problem():
+    g = load_golden("kat_epic203311200")
+    lc, pri = g["lc"], priors_from_table(g["priors"])
+    rng = np.random.default_rng(42)
+    W = 24
+    pos0 = g["params"][0][None, :] * (1 + 1e-4 * rng.standard_normal((W, 6)))
+    return lc, pri, pos0
+
+
+@pytest.mark.parametrize("mode", ["windowed", "brute"])
+def test_chain_matches_cpu_oracle_draw_by_draw(nb, mode):
+    from oracle import namaste_oracle as o, stretch_oracle as so
+    lc, pri, pos0 = _problem()
+    nsteps, seed = 25, 20261019
+    ref_chain, ref_ln, ref_acc = so.run(lambda p: o.lnprob_ensemble(p, lc, pri), pos0, nsteps, seed)
+    s = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri, nb.MonotransitModel(*pos0[0])), mode=mode, seed=seed)
+    pos, lnp, _ = s.run_mcmc(pos0, nsteps)
+    assert s.chain.shape == (24, nsteps, 6) and s.lnprobability.shape == (24, nsteps)
+    # proposals are bit-identical as long as the accept decisions agree; they can only differ when
+    # |lnpdiff - ln u| ~ 1e-12, which a 25-step chain does not hit
+    assert np.array_equal(s.chain, ref_chain)
+    assert np.allclose(s.lnprobability, ref_ln, rtol=1e-12, atol=0)
+    assert np.array_equal(s.naccepted, ref_acc)
+    assert np.array_equal(pos, ref_chain[:, -1, :]) and np.allclose(lnp, ref_ln[:, -1], rtol=1e-12)
+    assert 0.1 < s.acceptance_fraction.mean() < 0.9
+
+
+def test_run_mcmc_appends_and_reset(nb):
+    lc, pri, pos0 = _problem()
+    s = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri), seed=7)
+    s.run_mcmc(pos0, 1)
+    s.run_mcmc(pos0, 9)          # namaste.py:592-594 calls run_mcmc twice from the same start: T = 1 + nsteps
+    assert s.chain.shape == (24, 10, 6) and s.iterations == 10
+    one = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri), seed=7)
+    one.run_mcmc(pos0, 4)
+    one.run_mcmc(None, 6)        # continue from the last state
+    assert one.chain.shape == (24, 10, 6)
+    straight = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri), seed=7)
+    straight.run_mcmc(pos0, 10)
+    assert np.array_equal(one.chain, straight.chain)     # counter-based RNG: splitting a run changes nothing
+    assert one.flatchain.shape == (240, 6) and one.flatlnprobability.shape == (240,)
+    one.reset()
+    assert one.chain.shape == (24, 0, 6) and one.iterations == 0
+    thin = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri), seed=7)
+    thin.run_mcmc(pos0, 10, thin=5)
+    assert np.array_equal(thin.chain, straight.chain[:, ::5, :])
+
+
+def test_emcee_error_contract(nb):
+    lc, pri, pos0 = _problem()
+    with pytest.raises(TypeError):
+        nb.EnsembleSampler(24, 6, lambda p: 0.0, args=(lc, pri))
+    with pytest.raises(AssertionError):
+        nb.EnsembleSampler(23, 6, nb.MonoOnlyLogProb, args=(lc, pri))
+    with pytest.raises(AssertionError):
+        nb.EnsembleSampler(10, 6, nb.MonoOnlyLogProb, args=(lc, pri))
+    s = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri), seed=1)
+    with pytest.raises(ValueError):
+        s.run_mcmc(None, 1)
+    bad = pos0.copy()
+    bad[3, 2] = np.nan
+    with pytest.raises(ValueError):
+        s.run_mcmc(bad, 1)
+    bad = pos0.copy()
+    bad[3, 4] = np.inf
+    with pytest.raises(ValueError):
+        s.run_mcmc(bad, 1)
+
+
+def test_posterior_agrees_with_cpu_chain_statistically(nb):
+    """Different seeds on CPU and GPU: posterior medians must agree within Monte-Carlo error."""
+    from oracle import namaste_oracle as o, stretch_oracle as so
+    lc, pri, pos0 = _problem()
+    rng = np.random.default_rng(3)
+    pos0 = np.repeat(pos0[:1], 32, axis=0) * (1 + 1e-4 * rng.standard_normal((32, 6)))
+    nsteps = 600
+    s = nb.EnsembleSampler(32, 6, nb.MonoOnlyLogProb, args=(lc, pri), seed=111)
+    s.run_mcmc(pos0, nsteps)
+    gpu = s.chain[:, nsteps // 2:, :].reshape(-1, 6)
+    cpu_chain, _, _ = so.run(lambda p: o.lnprob_ensemble(p, lc, pri), pos0, nsteps, 222)
+    cpu = cpu_chain[:, nsteps // 2:, :].reshape(-1, 6)
+    for d in range(6):
+        sd = 0.5 * (gpu[:, d].std() + cpu[:, d].std())
+        # ~ (32 walkers * 300 steps) / tau(~60) independent samples per chain -> s.e. ~ sd / 12
+        assert abs(np.median(gpu[:, d]) - np.median(cpu[:, d])) < 0.5 * sd, d
