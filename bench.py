@@ -296,6 +296,24 @@ def run_ours(args):
     device_loop("windowed", max(args.warmup, 3))
     ms_win, _, _ = device_loop("windowed", args.steps)
     ms_win = max_over_ranks(ms_win)
+    ref_f64 = out.cpu().numpy().copy()
+    # FP32 variant (reported separately): windowed stage 1 + FP32 transit model in stage 2
+    def device_loop_f32(steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record(stream)
+            staged.lnprob_device(d_pos, d_pri, out=out, mode="windowed", dtype="f32")
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    device_loop_f32(max(args.warmup, 3))
+    ms_f32 = max_over_ranks(device_loop_f32(args.steps))
+    f32_out = out.cpu().numpy().copy()
+    fin = np.isfinite(ref_f64) & (np.abs(ref_f64) < 1e15)
+    f32_err = float(np.max(np.abs(f32_out[fin] - ref_f64[fin]) / np.abs(ref_f64[fin])))
+    staged.lnprob_device(d_pos, d_pri, out=out, mode="windowed")  # leave the FP64 result in `out`
     ref_out = out.cpu().numpy().copy()
 
     # ---- end to end through the public host API (numpy in / numpy out) -----------------------
@@ -369,6 +387,9 @@ def run_ours(args):
                      "ms_per_step": ms_win / args.steps, "speedup_vs_brute": ms_brute / ms_win,
                      "e2e": units / (dt_e2e_win / args.steps),
                      "note": "exact prefix-sum + in-transit-window kernel; effective wt/s, not a roofline figure"},
+        "fp32": {"value": units / (ms_f32 / args.steps * 1e-3), "unit": "wt/s", "ms_per_step": ms_f32 / args.steps,
+                 "max_rel_err_vs_fp64": f32_err,
+                 "note": "NMB_F32: FP32 transit model (depth space) in the windowed pipeline; reported separately"},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": traffic,
                      "peak_source": "DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 entry)",

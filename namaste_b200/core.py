@@ -7,7 +7,9 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import MODES, F64, as_f64, check, load, ptr
+from ._lib import MODES, F64, F32, as_f64, check, load, ptr
+
+DTYPES = {"f64": F64, "f32": F32, F64: F64, F32: F32, "float64": F64, "float32": F32}
 
 PARAM_NAMES = ("tcen", "b", "vel", "RpRs", "LD1", "LD2")  # namaste/namaste.py:1153
 _PRIOR_KINDS = {"gaussian": 1.0, "normlim": 2.0, "evans": 3.0}
@@ -85,7 +87,7 @@ class LightCurve:
             pass
 
     # ---- host-buffer path (the call a reference user makes) --------------------------------
-    def lnprob(self, params, priors=None, mode="windowed", return_loglike=False):
+    def lnprob(self, params, priors=None, mode="windowed", return_loglike=False, dtype="f64"):
         """Ensemble log-probability.  ``params`` is [W, 6] (single light curve) or
         [ncand, W, 6]; returns [W] / [ncand, W] (and the bare log-likelihood if asked)."""
         lib = load()
@@ -103,14 +105,15 @@ class LightCurve:
             tab = np.ascontiguousarray(np.broadcast_to(tab, (self.ncand, 6, 6)))
         out = np.empty((self.ncand, W))
         ll = np.empty((self.ncand, W)) if return_loglike else None
-        check(lib.nmb_lnprob_host(self._h, ptr(p), W, ptr(tab), ptr(out), ptr(ll), MODES[mode], F64), "lnprob")
+        check(lib.nmb_lnprob_host(self._h, ptr(p), W, ptr(tab), ptr(out), ptr(ll), MODES[mode], DTYPES[dtype]), "lnprob")
         if squeeze:
             out = out[0]
             ll = ll[0] if ll is not None else None
         return (out, ll) if return_loglike else out
 
     # ---- device-buffer path (torch tensors stay on the GPU) ---------------------------------
-    def lnprob_device(self, params, priors=None, out=None, loglike=None, mode="windowed", stream=None):
+    def lnprob_device(self, params, priors=None, out=None, loglike=None, mode="windowed", stream=None,
+                      dtype="f64"):
         """Asynchronous evaluation on torch CUDA tensors: params [ncand*W*6] float64,
         priors [ncand, 6, 6] float64 tensor or None.  Returns the output tensor."""
         import torch
@@ -122,7 +125,7 @@ class LightCurve:
             out = torch.empty((self.ncand, W), dtype=torch.float64, device=params.device)
         if stream is None:
             stream = torch.cuda.current_stream(params.device).cuda_stream
-        check(lib.nmb_lnprob(self._h, ptr(params), W, ptr(priors), ptr(out), ptr(loglike), MODES[mode], F64,
+        check(lib.nmb_lnprob(self._h, ptr(params), W, ptr(priors), ptr(out), ptr(loglike), MODES[mode], DTYPES[dtype],
                              ctypes.c_void_p(stream)), "lnprob_device")
         return out
 

@@ -331,10 +331,10 @@ EvalShape eval_shape(int S, size_t CW) {
     return {best, item};
 }
 
-template <int S, int MINB>
+template <int S, int MINB, int PATH>
 int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                    cudaStream_t st, const nmb::SampleCtx& sc) {
-    auto kern = nmb::eval_ranges_kernel<S, kEvalThreads, MINB, true>;
+    auto kern = nmb::eval_ranges_kernel<S, kEvalThreads, MINB, PATH>;
     const size_t smem = sizeof(nmb::EvalSmem<S, kEvalThreads>);
     static thread_local int grid = 0;
     if (!grid) {
@@ -354,17 +354,14 @@ int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors
 
 template <int S>
 int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                cudaStream_t st, const nmb::SampleCtx& sc) {
-    static const int mb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 4;
-    if (mb == 6) return launch_eval_mb<S, 6>(lc, params, W, priors, lnprob, loglike, st, sc);
-    if (mb == 5) return launch_eval_mb<S, 5>(lc, params, W, priors, lnprob, loglike, st, sc);
-    if (mb == 3) return launch_eval_mb<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
-    return launch_eval_mb<S, 4>(lc, params, W, priors, lnprob, loglike, st, sc);
+                cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
+    if (dtype == NMB_F32) return launch_eval_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
+    return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
 
 template <int S>
 int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                 cudaStream_t st, const nmb::SampleCtx& sc) {
+                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     constexpr int WT = 8, MINB = 4;
     constexpr int kBlock = kThreads + 32;  // 4 consumer warps + 1 producer warp
     const int ntiles = (int)(lc->npad / kTile);
@@ -395,7 +392,7 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     g_launches++;
     CU(cudaGetLastError());
     g_timer.mark(1, st);
-    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc);
+    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     g_timer.mark(2, st);
     g_timer.done("brute");
     return rc;
@@ -403,7 +400,7 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
 
 template <int S>
 int launch_window(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                  cudaStream_t st, const nmb::SampleCtx& sc) {
+                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
     constexpr int kWinThreads = 64;
@@ -413,7 +410,7 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     g_launches++;
     CU(cudaGetLastError());
     g_timer.mark(1, st);
-    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc);
+    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     g_timer.mark(2, st);
     g_timer.done("windowed");
     return rc;
@@ -482,13 +479,14 @@ static int lnprob_impl(nmb_lc* lc, const double* params, int64_t W, const double
                        double* loglike, int mode, int dtype, void* stream, const nmb::SampleCtx& sc) {
     if (!lc || !params || (!lnprob && !sc.enabled)) return fail(NMB_ERR_ARG, "nmb_lnprob: null pointer");
     if (W < 1 || W > (1 << 24)) return fail(NMB_ERR_ARG, "nmb_lnprob: W out of range");
-    if (dtype != NMB_F64) return fail(NMB_ERR_ARG, "nmb_lnprob: only NMB_F64 is implemented in this build");
+    if (dtype != NMB_F64 && dtype != NMB_F32) return fail(NMB_ERR_ARG, "nmb_lnprob: dtype must be NMB_F64 or NMB_F32");
+    if (dtype == NMB_F32 && mode == NMB_MODE_FUSED) return fail(NMB_ERR_ARG, "nmb_lnprob: NMB_MODE_FUSED is FP64 only");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = NMB_OK;
     if (mode == NMB_MODE_BRUTE) {
-        NMB_DISPATCH_S(lc->S, rc = launch_sweep<SS>(lc, params, (int)W, priors, lnprob, loglike, st, sc));
+        NMB_DISPATCH_S(lc->S, rc = launch_sweep<SS>(lc, params, (int)W, priors, lnprob, loglike, st, sc, dtype));
     } else if (mode == NMB_MODE_WINDOWED) {
-        NMB_DISPATCH_S(lc->S, rc = launch_window<SS>(lc, params, (int)W, priors, lnprob, loglike, st, sc));
+        NMB_DISPATCH_S(lc->S, rc = launch_window<SS>(lc, params, (int)W, priors, lnprob, loglike, st, sc, dtype));
     } else if (mode == NMB_MODE_FUSED) {
         NMB_DISPATCH_S(lc->S, rc = launch_fused<SS>(lc, params, (int)W, priors, lnprob, loglike, st));
     } else {

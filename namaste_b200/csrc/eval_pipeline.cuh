@@ -516,15 +516,18 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
 // (fixed order), adds the priors and writes lnprob.
 constexpr int kMaxTSW = 32;
 
-template <bool FAST>
-__device__ __forceinline__ double sample_flux_eval(double ti, double offk, const WalkerConsts& wc);
+// PATH: 0 = general IEEE FP64, 1 = FP64 hot path (default), 2 = FP32 hot path (NMB_F32)
+template <int PATH>
+__device__ __forceinline__ double sample_flux_eval(double ti, double offk, const WalkerConsts& wc,
+                                                   const QuadConstsF& cf);
 
 __device__ __noinline__ double sample_flux_slowpath(double z, const QuadConsts* q) {
     return occultquad_point<false, IeeeOps>(z, *q, nullptr, nullptr, nullptr);
 }
 
 template <>
-__device__ __forceinline__ double sample_flux_eval<true>(double ti, double offk, const WalkerConsts& wc) {
+__device__ __forceinline__ double sample_flux_eval<1>(double ti, double offk, const WalkerConsts& wc,
+                                                      const QuadConstsF&) {
     const double ft = ti + offk;
     const double x = ft - wc.tcen;
     const double vx = wc.vel * x;
@@ -541,8 +544,24 @@ __device__ __forceinline__ double sample_flux_eval<true>(double ti, double offk,
     return F;
 }
 template <>
-__device__ __forceinline__ double sample_flux_eval<false>(double ti, double offk, const WalkerConsts& wc) {
+__device__ __forceinline__ double sample_flux_eval<0>(double ti, double offk, const WalkerConsts& wc,
+                                                      const QuadConstsF&) {
     return sample_flux(ti, offk, wc);
+}
+template <>
+__device__ __forceinline__ double sample_flux_eval<2>(double ti, double offk, const WalkerConsts& wc,
+                                                      const QuadConstsF& cf) {
+    const double ft = ti + offk;
+    const double x = ft - wc.tcen;          // FP64 difference of the absolute times, then FP32
+    const float vx = (float)wc.vel * (float)x;
+    const float zf = sqrtf(fmaf(vx, vx, (float)wc.b2));
+    if (zf > cf.onep * 1.000001f) return wc.q.fout;
+    float depth;
+    if (occultquad_hot_f32(zf, cf, depth) && fabsf(depth) <= 1e30f) return 1.0 - (double)depth;
+    // anything else (other cases, exact limb, non-finite): the FP64 general path
+    const double vxd = wc.vel * x;
+    const double zz = ::sqrt(wc.b2 + vxd * vxd);
+    return (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, &wc.q);
 }
 
 template <int S, int THREADS>
@@ -566,7 +585,7 @@ __device__ __forceinline__ ItemMeta load_item_meta(const EvalWs& ws, int item, i
     return m;
 }
 
-template <int S, int THREADS, int MINB, bool FAST>
+template <int S, int THREADS, int MINB, int PATH>
 __global__ void __launch_bounds__(THREADS, MINB)
 eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
                    int TSW, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
@@ -601,6 +620,7 @@ eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const do
         const int cw = cur.cw;
         const int cand = cw / W;
         const WalkerConsts wc = ws.wcs[cw];
+        const QuadConstsF cf = (PATH == 2) ? to_f32(wc.q) : QuadConstsF{};
         const int ci = item - cur.first;
         const int n_w = cur.hi - cur.lo;
         int clen = (n_w + cur.nch - 1) / cur.nch;
@@ -618,7 +638,7 @@ eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const do
             const int nsamp = nts * Sx;
             for (int j = lane; j < nsamp; j += 32) {
                 const int h = j / Sx, k = j - h * Sx;
-                scratch[h * SP + k] = sample_flux_eval<FAST>(__ldg(gt + sub + h), __ldg(goff + k), wc);
+                scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + sub + h), __ldg(goff + k), wc, cf);
             }
             __syncwarp();
             if (lane < nts) {

@@ -136,7 +136,7 @@ def MonoLnPrior(params, priors):
     return core.lnprior(params, priors)
 
 
-def MonoOnlyLogProb(params, lc, priors, monomodel=None, mode="windowed"):
+def MonoOnlyLogProb(params, lc, priors, monomodel=None, mode="windowed", dtype="f64"):
     """Gaussian (no-GP) log-probability of the single-transit model (namaste.py:1345-1349).
 
     ``params`` may be one vector [6] (returns a float, exactly the reference's contract) or
@@ -148,12 +148,12 @@ def MonoOnlyLogProb(params, lc, priors, monomodel=None, mode="windowed"):
     if p.ndim == 1:
         if monomodel is not None:
             monomodel.set_parameter_vector(p)  # the reference mutates the model (namaste.py:1346)
-        return float(staged.lnprob(p[None, :], priors, mode=mode)[0])
-    return staged.lnprob(p, priors, mode=mode)
+        return float(staged.lnprob(p[None, :], priors, mode=mode, dtype=dtype)[0])
+    return staged.lnprob(p, priors, mode=mode, dtype=dtype)
 
 
-def MonoOnlyNegLogProb(params, lc, priors, monomodel=None, mode="windowed"):
-    return -1 * MonoOnlyLogProb(params, lc, priors, monomodel, mode=mode)
+def MonoOnlyNegLogProb(params, lc, priors, monomodel=None, mode="windowed", dtype="f64"):
+    return -1 * MonoOnlyLogProb(params, lc, priors, monomodel, mode=mode, dtype=dtype)
 
 
 def CalcTdur(vel, b, p):
