@@ -339,7 +339,8 @@ def run_ours(args):
     n_mcmc = 20 if args.profile else 200
     for mode in ("windowed", "brute"):
         smp = nb.EnsembleSampler(W, 6, nb.MonoOnlyLogProb, args=(staged, wl["priors"]), mode=mode, seed=1 + rank)
-        smp.run_mcmc(wl["pos"], 10)
+        smp.run_mcmc(wl["pos"], n_mcmc)     # warm-up: also grows the device-resident chain to its final capacity
+        smp.reset()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

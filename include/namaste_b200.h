@@ -128,6 +128,8 @@ void* nmb_sampler_stream(nmb_sampler* s);
 /* ---- measurement helpers (used by bench.py) ------------------------------------------------ */
 /* Sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), CUDA-event timed. */
 int nmb_measure_fp64_peak(double* tflops, double* ms);
+/* diagnostics: phase envelopes (globaltimer ns) of the last evaluation; needs NMB_TRACE=1 in the environment */
+int nmb_debug_trace(nmb_lc* lc, uint64_t* out16);
 /* number of kernels this library has launched so far in this process */
 int64_t nmb_launch_count(void);
 

@@ -8,6 +8,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnamaste_b200.so")
+if os.environ.get("NMB_LIB"):  # diagnostics: A/B builds of the same library
+    LIB_PATH = os.environ["NMB_LIB"]
 
 NMB_OK, NMB_ERR_ARG, NMB_ERR_CUDA, NMB_ERR_PRECOND, NMB_ERR_NAN = 0, -1, -2, -3, -4
 MODE_BRUTE, MODE_WINDOWED, MODE_FUSED = 0, 1, 2
@@ -52,6 +54,7 @@ SIGNATURES = {
     "nmb_sampler_devptr": (_vp, [_vp, ctypes.c_int]),
     "nmb_sampler_stream": (_vp, [_vp]),
     "nmb_measure_fp64_peak": (ctypes.c_int, [_c_double_p, _c_double_p]),
+    "nmb_debug_trace": (ctypes.c_int, [_vp, _vp]),
     "nmb_launch_count": (ctypes.c_int64, []),
 }
 

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/namaste_b200.h"
@@ -32,16 +33,18 @@ int cuda_fail(cudaError_t e, const char* what) {
 constexpr int kThreads = 128;  // sweep / window block size
 constexpr int kTPT = 4;        // timestamps per thread in the sweep -> 512-timestamp tiles
 constexpr int kTile = kThreads * kTPT;
+constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-thread sweep
 
 }  // namespace
 
 struct nmb_lc {
     int64_t ncand = 0, nmax = 0, npad = 0;
     int S = 0;
+    int gran = 64, ngran = 0;
     int device = 0;
     std::vector<int64_t> n;
     std::vector<double> cad;
-    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
+    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_term = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
     long long* d_n = nullptr;
     int *d_tgrid = nullptr, *d_gcount = nullptr;
     double *d_t0 = nullptr, *d_ginv = nullptr;
@@ -60,7 +63,7 @@ struct nmb_lc {
 
     nmb::LcView view() const {
         nmb::LcView v;
-        v.t = d_t; v.f = d_f; v.w = d_w; v.pre_hi = d_pre_hi; v.pre_lo = d_pre_lo; v.off = d_off;
+        v.t = d_t; v.f = d_f; v.w = d_w; v.term = d_term; v.gran = gran; v.ngran = ngran; v.pre_hi = d_pre_hi; v.pre_lo = d_pre_lo; v.off = d_off;
         v.n = d_n; v.npad = npad; v.ncand = (int)ncand; v.S = S;
         v.tgrid = d_tgrid; v.t0 = d_t0; v.ginv = d_ginv; v.gcount = d_gcount; v.gstride = gstride;
         return v;
@@ -73,12 +76,12 @@ extern "C" int64_t nmb_launch_count(void) { return g_launches.load(); }
 
 extern "C" void nmb_lc_destroy(nmb_lc* lc) {
     if (!lc) return;
-    cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
+    cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_term); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
     cudaFree(lc->d_tgrid); cudaFree(lc->d_gcount); cudaFree(lc->d_t0); cudaFree(lc->d_ginv);
     cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
-    cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.lp); cudaFree(lc->ws.wcs); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
-    cudaFree(lc->ws.blkstart); cudaFree(lc->ws.itemwalker); cudaFree(lc->ws.itempart); cudaFree(lc->ws.itemsdone);
-    cudaFree(lc->ws.grouptick); cudaFree(lc->ws.counters); cudaFree(lc->ws.tilectr);
+    cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.wcs); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
+    cudaFree(lc->ws.nslots); cudaFree(lc->ws.slots); cudaFree(lc->ws.slotpart); cudaFree(lc->ws.slotsdone);
+    cudaFree(lc->ws.grouptick); cudaFree(lc->ws.counters); cudaFree(lc->ws.trace);
     if (lc->h_pin) cudaFreeHost(lc->h_pin);
     if (lc->own_stream) cudaStreamDestroy(lc->own_stream);
     delete lc;
@@ -99,8 +102,13 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
         if (n[c] > stride) return fail(NMB_ERR_ARG, "nmb_lc_create: n[c] > stride");
         nmax = std::max(nmax, n[c]);
     }
-    const int64_t npad = (nmax + kTile - 1) / kTile * kTile;
-    std::vector<double> ht(ncand * npad, 0.0), hf(ncand * npad, 1.0), hw(ncand * npad, 0.0);
+    // reduction granule of the brute-force sweep: a power of two >= 64 timestamps chosen from the
+    // light-curve length alone (<= 512 granules), so partial sums do not depend on the launch shape
+    int gran = kSweepChunk;
+    while ((nmax + gran - 1) / gran > 512) gran *= 2;
+    const int64_t padto = std::max<int64_t>(kTile, gran);
+    const int64_t npad = (nmax + padto - 1) / padto * padto;
+    std::vector<double> ht(ncand * npad, 0.0), hf(ncand * npad, 1.0), hw(ncand * npad, 0.0), hterm(ncand * npad, 0.0);
     std::vector<double> hph(ncand * (npad + 1), 0.0), hpl(ncand * (npad + 1), 0.0), hoff(ncand * S, 0.0);
     std::vector<double> cads(ncand);
     std::vector<double> d;
@@ -145,6 +153,7 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
             hpl[c * (npad + 1) + i] = pl;
             const double r = fc[i] - 1.0;
             const double term = w * (r * r);
+            hterm[c * npad + i] = term;
             const double s = ph + term;
             const double bb = s - ph;
             const double e = (ph - (s - bb)) + (term - bb);
@@ -194,6 +203,7 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
 
     nmb_lc* lc = new nmb_lc;
     lc->ncand = ncand; lc->nmax = nmax; lc->npad = npad; lc->S = S; lc->gstride = gstride;
+    lc->gran = gran; lc->ngran = (int)(npad / gran);
     lc->n.assign(n, n + ncand);
     lc->cad = cads;
     cudaGetDevice(&lc->device);
@@ -205,7 +215,7 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
     };
     cudaError_t e = cudaSuccess;
     if ((e = up(&lc->d_t, ht)) != cudaSuccess || (e = up(&lc->d_f, hf)) != cudaSuccess ||
-        (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
+        (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_term, hterm)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
         (e = up(&lc->d_pre_lo, hpl)) != cudaSuccess || (e = up(&lc->d_off, hoff)) != cudaSuccess ||
         (e = up(&lc->d_t0, ht0)) != cudaSuccess || (e = up(&lc->d_ginv, hginv)) != cudaSuccess ||
         (e = cudaMalloc(&lc->d_tgrid, hgrid.size() * sizeof(int))) != cudaSuccess ||
@@ -242,6 +252,21 @@ int set_smem(K kernel, size_t bytes) {
 
 constexpr int kEvalThreads = 128;
 
+// Launch with programmatic dependent launch enabled (see pdl_wait / pdl_trigger): the kernel may be
+// scheduled while its predecessor in the stream drains.  NMB_NO_PDL=1 restores plain launches.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool off = std::getenv("NMB_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // NMB_STAGE_TIMING=1: time stage 1 / stage 2 separately with CUDA events (diagnostics only)
 struct StageTimer {
     bool on = false;
@@ -272,32 +297,35 @@ StageTimer g_timer;
 int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
     nmb::EvalWs& ws = lc->ws;
     if (CW > lc->ws_cw) {
-        cudaFree(ws.oot); cudaFree(ws.lp); cudaFree(ws.wcs); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.blkstart);
-        cudaFree(ws.itemwalker); cudaFree(ws.itempart); cudaFree(ws.itemsdone); cudaFree(ws.grouptick);
-        cudaFree(ws.counters); cudaFree(ws.tilectr);
+        cudaFree(ws.oot); cudaFree(ws.wcs); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.nslots);
+        cudaFree(ws.slots); cudaFree(ws.slotpart); cudaFree(ws.slotsdone); cudaFree(ws.grouptick);
+        cudaFree(ws.counters); cudaFree(ws.trace);
+        cudaFree(ws.partials);
         ws = nmb::EvalWs{};
-        cudaFree(lc->ws.partials);
-        lc->ws.partials = nullptr;
         lc->ws_cw = 0; lc->ws_partials = 0;
-        const int maxch = (int)std::min<size_t>(256, std::max<size_t>(1, (size_t)4194304 / CW));
-        ws.maxch = maxch;
+        // timestamps per pass: as many whole bins as fit in kEvalPass supersamples; slots per walker:
+        // one pass each up to a pool of 4 M slots over the ensemble (>= 64 per walker)
+        ws.tsw = std::max(1, nmb::kEvalPass / lc->S);
+        const size_t full = (size_t)(lc->npad + ws.tsw - 1) / ws.tsw;
+        ws.maxslots = (int)std::min<size_t>(full, std::max<size_t>(64, (size_t)4194304 / CW));
+        const size_t cap = CW * ws.maxslots;
         CU(cudaMalloc(&ws.oot, CW * sizeof(double)));
-        CU(cudaMalloc(&ws.lp, CW * sizeof(double)));
         CU(cudaMalloc(&ws.wcs, CW * sizeof(nmb::WalkerConsts)));
         CU(cudaMalloc(&ws.rlo, CW * sizeof(int)));
         CU(cudaMalloc(&ws.rhi, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.itemsdone, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.blkstart, (CW + 1) * sizeof(int)));
-        CU(cudaMalloc(&ws.itemwalker, CW * maxch * sizeof(int)));
-        CU(cudaMalloc(&ws.itempart, CW * maxch * sizeof(double)));
+        CU(cudaMalloc(&ws.slotsdone, CW * sizeof(int)));
+        CU(cudaMalloc(&ws.nslots, CW * sizeof(int)));
+        CU(cudaMalloc(&ws.slots, cap * sizeof(nmb::SlotRec)));
+        CU(cudaMalloc(&ws.slotpart, cap * sizeof(double)));
         CU(cudaMalloc(&ws.grouptick, CW * sizeof(int)));
         CU(cudaMalloc(&ws.counters, 4 * sizeof(int)));
-        CU(cudaMalloc(&ws.tilectr, (size_t)lc->ncand * (lc->npad / kTile) * sizeof(int)));
-        ws.ntilectr = (int)(lc->ncand * (lc->npad / kTile));
-        CU(cudaMemsetAsync(ws.tilectr, 0, (size_t)ws.ntilectr * sizeof(int), st));
+        if (std::getenv("NMB_TRACE")) {
+            CU(cudaMalloc(&ws.trace, 16 * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(ws.trace, 0, 16 * sizeof(unsigned long long), st));
+        }
         CU(cudaMemsetAsync(ws.grouptick, 0, CW * sizeof(int), st));
         CU(cudaMemsetAsync(ws.counters, 0, 4 * sizeof(int), st));
-        nmb::init_ranges_kernel<<<(unsigned)((CW + 255) / 256), 256, 0, st>>>(ws.rlo, ws.rhi, ws.itemsdone, (int)CW);
+        nmb::init_ranges_kernel<<<(unsigned)((CW + 255) / 256), 256, 0, st>>>(ws.rlo, ws.rhi, ws.slotsdone, (int)CW);
         g_launches++;
         CU(cudaGetLastError());
         lc->ws_cw = CW;
@@ -311,44 +339,23 @@ int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
     return NMB_OK;
 }
 
-// timestamps a warp evaluates per pass (TSW) and per work item (item_ts) for supersampling S:
-// smallest TSW whose S*TSW samples fill >= 90% of the 32-lane rounds they occupy
-struct EvalShape { int tsw, item_ts; };
-EvalShape eval_shape(int S, size_t CW) {
-    int best = 32;
-    for (int t = 1; t <= nmb::kMaxTSW; ++t) {
-        const int ns = t * S, rounds = (ns + 31) / 32;
-        if (ns >= 0.9 * rounds * 32) { best = t; break; }
-    }
-    // item size: about three items per resident warp for a typical ~40-timestamp transit, so that
-    // small ensembles are spread over the GPU and large ones keep one item per walker
-    const double want = 40.0 * (double)CW / (3.0 * 148 * 16);
-    int item = best;
-    while (item * S < 64 || item < want) item += best;
-    if (item > 64 * best) item = 64 * best;
-    static const int force = std::getenv("NMB_ITEM_TS") ? std::atoi(std::getenv("NMB_ITEM_TS")) : 0;
-    if (force > 0) item = (force + best - 1) / best * best;
-    return {best, item};
-}
-
 template <int S, int MINB, int PATH>
 int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                    cudaStream_t st, const nmb::SampleCtx& sc) {
-    auto kern = nmb::eval_ranges_kernel<S, kEvalThreads, MINB, PATH>;
-    const size_t smem = sizeof(nmb::EvalSmem<S, kEvalThreads>);
-    static thread_local int grid = 0;
+    auto kern = nmb::eval_slots_kernel<S, kEvalThreads, MINB, PATH>;
+    const size_t smem = sizeof(nmb::EvalSmem<kEvalThreads>);
+    static thread_local int grid = 0, sms = 0;
     if (!grid) {
         if (int rc = set_smem(kern, smem)) return rc;
-        int dev = 0, sms = 0, per_sm = 0;
+        int dev = 0, per_sm = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEvalThreads, smem));
-        grid = sms * std::max(per_sm, 1);
+        grid = sms * std::max(per_sm, 1);  // one resident wave
     }
-    kern<<<grid, kEvalThreads, smem, st>>>(lc->view(), params, W, priors, lc->ws,
-                                           eval_shape(lc->S, (size_t)lc->ncand * W).tsw, lnprob, loglike, sc);
+    CU(launch_pdl(kern, dim3(grid), dim3(kEvalThreads), smem, st, lc->view(), params, W, priors, lc->ws, sms, lnprob,
+                  loglike, sc));
     g_launches++;
-    CU(cudaGetLastError());
     return NMB_OK;
 }
 
@@ -356,43 +363,53 @@ template <int S>
 int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     if (dtype == NMB_F32) return launch_eval_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
+    static const int minb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 4;
+    if (minb == 5) return launch_eval_mb<S, 5, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (minb == 6) return launch_eval_mb<S, 6, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
     return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
+}
+
+template <int S, int THREADS, int MINB>
+int launch_sweep_t(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                   cudaStream_t st, const nmb::SampleCtx& sc) {
+    auto kern = nmb::sweep_walkers_kernel<S, THREADS, kSweepChunk, MINB>;
+    const size_t smem = sizeof(nmb::WalkSmem<S, kSweepChunk>);
+    static thread_local bool ready = false;
+    if (!ready) {
+        if (int rc = set_smem(kern, smem)) return rc;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ready = true;
+    }
+    const size_t CW = (size_t)lc->ncand * W;
+    const int nwb = (W + THREADS - 1) / THREADS;
+    // granules per block: about eight resident warps per SM sub-partition over the whole grid
+    const long long warps = (long long)lc->ncand * nwb * (THREADS / 32) * lc->ngran;
+    static const int force_gpb = std::getenv("NMB_GPB") ? std::atoi(std::getenv("NMB_GPB")) : 0;
+    int gpb = (int)std::max<long long>(1, (warps + 592LL * 8 - 1) / (592LL * 8));
+    if (force_gpb > 0) gpb = force_gpb;
+    gpb = std::min(gpb, lc->ngran);
+    const int ntb = (lc->ngran + gpb - 1) / gpb;
+    dim3 grid(ntb, nwb, (unsigned)lc->ncand);
+    CU(launch_pdl(kern, grid, dim3(THREADS), smem, st, lc->view(), params, W, gpb, priors, lc->ws, lnprob, loglike, sc));
+    g_launches++;
+    return NMB_OK;
 }
 
 template <int S>
 int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
-    constexpr int WT = 8, MINB = 4;
-    constexpr int kBlock = kThreads + 32;  // 4 consumer warps + 1 producer warp
-    const int ntiles = (int)(lc->npad / kTile);
     const size_t CW = (size_t)lc->ncand * W;
-    if (int rc = ensure_ws(lc, CW, ntiles, st)) return rc;
-    const int groups = (W + WT - 1) / WT;
-    auto kern = nmb::sweep_classify_kernel<S, kThreads, kTPT, WT, MINB>;
-    const size_t smem = sizeof(nmb::ClassifySmem<S, kThreads, kTPT, WT>);
-    static thread_local int slots = 0;
-    if (!slots) {
-        if (int rc = set_smem(kern, smem)) return rc;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        int dev = 0, sms = 0, per_sm = 0;
-        CU(cudaGetDevice(&dev));
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
-        slots = sms * std::max(per_sm, 1);
-    }
-    // one resident wave: blocks of a tile share its queue of walker groups
-    const long long per_tile = std::max<long long>(1, slots / ((long long)ntiles * lc->ncand));
-    const int by = (int)std::min<long long>(groups, per_tile);
-    dim3 grid(ntiles, by, (unsigned)lc->ncand);
+    if (int rc = ensure_ws(lc, CW, lc->ngran, st)) return rc;
     g_timer.mark(0, st);
-    nmb::walker_setup_kernel<<<(unsigned)((CW + 63) / 64), 64, 0, st>>>(lc->view(), params, W, priors, lc->ws, sc);
-    g_launches++;
-    kern<<<grid, kBlock, smem, st>>>(lc->view(), params, W, groups, priors, lc->ws,
-                                       eval_shape(lc->S, CW).item_ts, lnprob, loglike, sc);
-    g_launches++;
-    CU(cudaGetLastError());
+    // 128-walker blocks when they alone fill the GPU, single-warp blocks (finer spread) otherwise
+    static const int force_thr = std::getenv("NMB_SWEEP_THREADS") ? std::atoi(std::getenv("NMB_SWEEP_THREADS")) : 0;
+    const long long blocks128 = (long long)lc->ncand * ((W + 127) / 128) * lc->ngran;
+    const bool wide = force_thr ? (force_thr == 128) : (W >= 128 || blocks128 >= 4 * 148);
+    int rc = wide ? launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc)
+                  : launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (rc) return rc;
     g_timer.mark(1, st);
-    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
+    rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     g_timer.mark(2, st);
     g_timer.done("brute");
     return rc;
@@ -405,10 +422,9 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
     constexpr int kWinThreads = 64;
     g_timer.mark(0, st);
-    nmb::window_ranges_kernel<kWinThreads><<<(unsigned)((CW + kWinThreads - 1) / kWinThreads), kWinThreads, 0, st>>>(
-        lc->view(), params, W, priors, lc->ws, eval_shape(lc->S, (size_t)lc->ncand * W).item_ts, lnprob, loglike, sc);
+    CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),
+                  dim3(kWinThreads), 0, st, lc->view(), params, W, priors, lc->ws, lnprob, loglike, sc));
     g_launches++;
-    CU(cudaGetLastError());
     g_timer.mark(1, st);
     const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     g_timer.mark(2, st);
@@ -560,6 +576,20 @@ extern "C" int nmb_lnprior(const double* params, int64_t W, int npar, const doub
     nmb::lnprior_kernel<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(params, W, npar, priors, lnprior);
     g_launches++;
     CU(cudaGetLastError());
+    return NMB_OK;
+}
+
+// Diagnostics (NMB_TRACE=1): phase envelopes of the last evaluation in globaltimer nanoseconds.
+// out[0]/out[8] earliest block start of stage 1/2, other slots the latest end of a phase; the
+// slots are re-armed for the next evaluation.
+extern "C" int nmb_debug_trace(nmb_lc* lc, uint64_t* out) {
+    if (!lc || !out) return fail(NMB_ERR_ARG, "nmb_debug_trace: null pointer");
+    if (!lc->ws.trace) return fail(NMB_ERR_ARG, "nmb_debug_trace: tracing is off (set NMB_TRACE=1 before the first evaluation)");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, lc->ws.trace, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    uint64_t init[16] = {0};
+    init[0] = init[8] = ~0ull;
+    CU(cudaMemcpy(lc->ws.trace, init, sizeof init, cudaMemcpyHostToDevice));
     return NMB_OK;
 }
 

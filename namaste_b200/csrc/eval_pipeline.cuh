@@ -6,16 +6,18 @@
 // priors and writes lnprob.  Both stages are deterministic (fixed summation trees, integer
 // atomics only), so a chain is reproducible bit for bit.
 //
-//   sweep_classify_kernel (NMB_MODE_BRUTE)   : visits every supersample of every timestamp:
-//       grid = (time tile, walker group, candidate); the tile's (t, flux, w) are staged in shared
-//       memory by TMA bulk copies and reused by all walkers of the group; 5 FP64 ops per sample
-//       (t+off, -tcen, *vel, fma, compare) decide "outside the limb"; out-of-transit chi^2 terms
-//       are accumulated on the fly; in-transit timestamps only widen the walker's [lo, hi) range.
-//   window_ranges_kernel  (NMB_MODE_WINDOWED): a warp per walker derives a conservative range from
-//       the geometry with a 32-ary search over t, and takes the out-of-transit chi^2 from the
-//       double-double prefix sums staged with the light curve.
-//   eval_ranges_kernel    (both)             : persistent blocks pull (walker, chunk) items; one
-//       thread per supersample, bins reduced in NumPy's order, residuals accumulated per item.
+//   sweep_walkers_kernel  (NMB_MODE_BRUTE)   : visits every supersample of every timestamp, one
+//       walker per thread; time chunks stream through shared memory by TMA bulk copies; two DFMA
+//       and a third of an integer min per sample decide "outside the limb"; out-of-transit chi^2
+//       terms are accumulated on the fly; in-transit timestamps only widen the walker's [lo, hi).
+//   window_ranges_kernel  (NMB_MODE_WINDOWED): a thread per walker derives a conservative range from
+//       the geometry with an O(1) lookup in a uniform time grid, and takes the out-of-transit chi^2
+//       from the double-double prefix sums staged with the light curve.
+//   eval_slots_kernel     (both)             : resident warps share the queue of slots (passes of
+//       one walker's range); one supersample per lane and round, bins reduced in NumPy's order,
+//       slot partials stored and folded in slot order by the warp that completes a walker.
+// Stage 1 pushes its walkers' slots with one atomicAdd per block; kernels are chained with
+// programmatic dependent launch so the next one is resident when its predecessor drains.
 //
 // Why a range is enough: along the sorted supersample sequence fl(t_i + off_k) - tcen is monotone,
 // so fma(vx, vx, b^2) is V-shaped and {q <= threshold} is contiguous.
@@ -29,24 +31,46 @@
 
 namespace nmb {
 
+// A *slot* is the unit of work and of summation in stage 2: a run of TSW-timestamp passes of one
+// walker's in-transit range (one pass unless the walker needs more than `maxslots` slots).  Slot
+// boundaries depend only on the walker's own range and on S, never on the launch shape, and each
+// slot's chi^2 partial is stored, so any partition of the slots over warps gives the same bits.
+struct SlotRec {
+    int cw;      // walker (candidate * W + walker)
+    int t0, t1;  // timestamps [t0, t1) of this slot
+    int first;   // first slot of the walker (its slots are contiguous in the queue)
+};
+
 struct EvalWs {
-    double* partials;    // [CW][ntiles]   out-of-transit chi^2 per (walker, tile)      (brute)
+    double* partials;    // [C][ngran][W]  out-of-transit chi^2 per (granule, walker)   (brute)
     double* oot;         // [CW]           out-of-transit chi^2 per walker
-    double* lp;          // [CW]           log-prior per walker (computed in stage 1)
     WalkerConsts* wcs;   // [CW]
     int* rlo;            // [CW]  first in-transit timestamp   (INT_MAX when idle)
     int* rhi;            // [CW]  one past the last            (0 when idle)
-    int* blkstart;       // [CW+1] exclusive scan of items per walker
-    int* itemwalker;     // [CW*maxch]
-    double* itempart;    // [CW*maxch]
-    int* itemsdone;      // [CW]  (0 when idle)
-    int* grouptick;      // [C*ngroups] (0 when idle)
-    int* counters;       // [0] groups/blocks finished (0 when idle), [1] total items of this launch,
-                         // [2] next item of the stage-2 queue
-    int* tilectr;        // [C*ntiles] next walker group of each tile (reset by stage 2)
-    int ntilectr;
-    int maxch;
+    int* nslots;         // [CW]  slots of each walker with work in stage 2
+    SlotRec* slots;      // [slotcap]  queue of slots (spans allocated by atomicAdd in stage 1)
+    double* slotpart;    // [slotcap]  chi^2 partial of each slot
+    int* slotsdone;      // [CW]  (0 when idle)
+    int* grouptick;      // [C*walker blocks] finished time blocks per walker group (0 when idle)
+    int* counters;       // [1] slots pushed by stage 1 (queue tail), [2] next dynamically assigned chunk,
+                         // [3] stage-2 blocks finished; the last stage-2 block zeroes them
+    int maxslots;        // slots per walker are capped; longer ranges put several passes in a slot
+    int tsw;             // timestamps per pass: as many whole bins as fit in kEvalPass supersamples
+    unsigned long long* trace;  // diagnostics (NMB_TRACE): [16] phase envelopes in globaltimer ns, else null
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// slot 0/8: earliest block start of stage 1/2 (atomicMin); other slots: latest time a phase ended
+__device__ __forceinline__ void trace_min(const EvalWs& ws, int slot) {
+    if (ws.trace) atomicMin(ws.trace + slot, gtimer());
+}
+__device__ __forceinline__ void trace_max(const EvalWs& ws, int slot) {
+    if (ws.trace) atomicMax(ws.trace + slot, gtimer());
+}
 
 // Every evaluated walker ends here exactly once: plain evaluation writes the outputs, sampler mode
 // runs the accept/reject step of the stretch move instead.
@@ -57,353 +81,269 @@ __device__ __forceinline__ void finish_walker(const SampleCtx& sc, long long cw,
     if (sc.enabled) accept_stretch(sc, (int)(cw / W), (int)(cw % W), W, ll + lp);
 }
 
-template <int S>
-__host__ __device__ constexpr int ts_per_block(int threads, int s_rt) {
-    return threads / (S > 0 ? S : s_rt);
-}
-
-__device__ __forceinline__ int items_for(int n_w, int tsb, int maxch) {
+// number of slots and passes per slot for an in-transit range of n_w timestamps
+__device__ __forceinline__ int slots_for(int n_w, int tsw, int maxslots, int& passes_per_slot) {
+    passes_per_slot = 1;
     if (n_w <= 0) return 0;
-    const int need = (n_w + tsb - 1) / tsb;
-    return need < maxch ? need : maxch;
+    const int npass = (n_w + tsw - 1) / tsw;
+    passes_per_slot = (npass + maxslots - 1) / maxslots;
+    return (npass + passes_per_slot - 1) / passes_per_slot;
 }
 
-// Exclusive scan over all CW walkers by ONE block (the last one of stage 1); fills blkstart,
-// itemwalker and counters[1].  Tiles of THREADS*8 walkers; warp-shuffle scans, no serial part.
+// Block-cooperative push onto the stage-2 queue: every thread brings the in-transit range of its
+// walker (empty for none); the block takes one contiguous span of the queue with a single atomicAdd
+// and each walker writes its slot records.  The order of spans in the queue depends on block
+// timing, results do not (see SlotRec).
 template <int THREADS>
-__device__ void scan_items(const EvalWs& ws, int CW, int item_ts, int* s_scan /*[THREADS/32 + 1]*/) {
-    constexpr int PER = 8, NWARP = THREADS / 32;
+__device__ __forceinline__ void push_slots(const EvalWs& ws, long long cw, int lo, int hi, int* s_scan /*[THREADS/32+1]*/) {
+    constexpr int NWARP = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int running = 0;
-    for (int base = 0; base < CW; base += THREADS * PER) {
-        const int i0 = base + tid * PER;
-        int cnt[PER];
-        int local = 0;
+    int pps;
+    const int mine = slots_for(hi - lo, ws.tsw, ws.maxslots, pps);
+    int incl = mine;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int i = i0 + j;
-            cnt[j] = (i < CW) ? items_for(__ldcg(ws.rhi + i) - __ldcg(ws.rlo + i), item_ts, ws.maxch) : 0;
-            local += cnt[j];
-        }
-        int incl = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        int woff = 0, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) {
-            const int v = s_scan[w];
-            if (w < warp) woff += v;
-            tile_total += v;
-        }
-        int run = running + woff + incl - local;
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int i = i0 + j;
-            if (i < CW) {
-                ws.blkstart[i] = run;
-                for (int c = 0; c < cnt[j]; ++c) ws.itemwalker[run + c] = i;
-                run += cnt[j];
-            }
-        }
-        running += tile_total;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
     if (tid == 0) {
-        ws.blkstart[CW] = running;
-        ws.counters[1] = running;
-        ws.counters[0] = 0;
-        ws.counters[2] = 0;
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < NWARP; ++i) {
+            const int v = s_scan[i];
+            s_scan[i] = tot;
+            tot += v;
+        }
+        s_scan[NWARP] = tot ? atomicAdd(ws.counters + 1, tot) : 0;
+    }
+    __syncthreads();
+    const int first = s_scan[NWARP] + s_scan[warp] + incl - mine;
+    const int step = pps * ws.tsw;
+    auto put = [&](int cwi, int lo_, int hi_, int first_, int step_, int i) {
+        SlotRec r;
+        r.cw = cwi; r.t0 = lo_ + i * step_; r.t1 = min(hi_, lo_ + (i + 1) * step_); r.first = first_;
+        *reinterpret_cast<int4*>(ws.slots + first_ + i) = *reinterpret_cast<const int4*>(&r);
+    };
+    if (mine > 0) {
+        ws.nslots[cw] = mine;
+        for (int i = 0; i < min(mine, 8); ++i) put((int)cw, lo, hi, first, step, i);
+    }
+    // walkers with long ranges (rare): the whole warp writes their remaining records
+    unsigned big = __ballot_sync(0xffffffffu, mine > 8);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int cw_b = __shfl_sync(0xffffffffu, (int)cw, src), lo_b = __shfl_sync(0xffffffffu, lo, src);
+        const int hi_b = __shfl_sync(0xffffffffu, hi, src), first_b = __shfl_sync(0xffffffffu, first, src);
+        const int step_b = __shfl_sync(0xffffffffu, step, src), n_b = __shfl_sync(0xffffffffu, mine, src);
+        for (int i = 8 + lane; i < n_b; i += 32) put(cw_b, lo_b, hi_b, first_b, step_b, i);
     }
 }
 
-// named barriers (id 0 is __syncthreads)
-__device__ __forceinline__ void bar_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(int id, int count) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-template <int S, int CTHREADS, int TPT, int WT>
-struct ClassifySmem {
-    static constexpr int TT = CTHREADS * TPT;
-    double t[TT], f[TT], w[TT];
-    double warpsum[2][WT][CTHREADS / 32];
+// ---- brute-force stage 1, walker-per-thread --------------------------------------------------
+// A block owns WPB*32 walkers (one per thread, constants in registers) and a span of `gpb`
+// reduction granules of one light curve.  The span streams through shared memory in chunks of CH
+// timestamps: two TMA bulk copies per chunk (t and the precomputed chi^2 terms w*(f-1)^2) into a
+// double buffer, from which the block builds the table of fine times ft[i][k] = t_i + off_k once
+// for all its walkers.  The inner loop then costs, per walker and fine sample, two DFMA
+//   vx' = fma(vel, ft, -vel*tcen),  q' = fma(vx', vx', b^2)
+// and a third of an integer 3-input min on the high words (VIMNMX3); ft arrives by broadcast
+// LDS.128, so the FP64 pipe is the only saturated unit.  A timestamp whose S samples all have
+// hi32(q') > hi32(q_thr) is provably outside the limb (see make_walker_consts) and adds its
+// precomputed term; the others only widen the walker's in-transit range, kept in registers and
+// merged with one atomicMin/Max per thread.  Per-(granule, walker) partial sums go to HBM
+// (coalesced) and are folded in granule order by the last block of each walker group, which makes
+// the result independent of the launch shape.
+template <int S, int CH>
+struct WalkSmem {
+    static constexpr int SR = S > 0 ? S : kMaxS;
+    static constexpr int SP = (SR + 1) & ~1;  // even row stride: 16-byte aligned rows for LDS.128
+    double ftab[2][CH * SP];
+    double traw[2][CH];
+    double term[2][CH];
     double off[kMaxS];
-    // per-walker classification constants, structure-of-arrays, double buffered across groups
-    double vel[2][WT], nvtc[2][WT], b2[2][WT], fbar[2][WT];
-    int qhi[2][WT];
-    unsigned long long mbar;
-    int group[2];
-    int s_scan[CTHREADS / 32 + 2];
-    int doscan;
+    unsigned long long mbar[2];
+    int s_scan[40];
+    int flag;
 };
 
-// Brute-force stage 1, warp specialised.  A block owns one time tile (staged once by TMA) and
-// pulls walker groups from the tile's queue.
-//   producer warp (the last one): fetches the next group, derives its walkers' constants one
-//     group ahead of the consumers, later publishes the group's tile partials, and - when this
-//     was the group's last tile - folds the tiles, evaluates the priors and settles walkers that
-//     never transit;
-//   consumer warps: per thread and timestamp the S fine times ft_k = t_i + off_k are formed once
-//     per group and shared by its WT walkers; per walker and fine sample the sweep costs two DFMA
-//     and one DSETP:  vx' = fma(vel, ft_k, -vel*tcen), q' = fma(vx', vx', b^2), outside iff
-//     q' > qthr_c.  They never wait for constants or reductions of other groups.
-template <int S, int CTHREADS, int TPT, int WT, int MINB>
-__global__ void __launch_bounds__(CTHREADS + 32, MINB)
-sweep_classify_kernel(LcView lc, const double* __restrict__ params, int W, int ngroups,
-                      const double* __restrict__ priors, EvalWs ws, int item_ts, double* __restrict__ lnprob,
-                      double* __restrict__ loglike, SampleCtx sc) {
-    constexpr int TT = CTHREADS * TPT;
-    constexpr int NCW = CTHREADS / 32;  // consumer warps
-    constexpr int ALL = CTHREADS + 32;
-    constexpr int SR = S > 0 ? S : kMaxS;
-    constexpr int BAR_FULL = 1, BAR_EMPTY = 3;  // +buf
+template <int S, int THREADS, int CH, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gpb,
+                     const double* __restrict__ priors, EvalWs ws, double* __restrict__ lnprob,
+                     double* __restrict__ loglike, SampleCtx sc) {
+    using Smem = WalkSmem<S, CH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ClassifySmem<S, CTHREADS, TPT, WT>& sm = *reinterpret_cast<ClassifySmem<S, CTHREADS, TPT, WT>*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, cand = blockIdx.z;
-    const int ntiles = gridDim.x;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x, wb = blockIdx.y, cand = blockIdx.z;
+    const int ntb = gridDim.x, nwb = gridDim.y;
     const int Sx = s_of<S>(lc.S);
-    const long long n = lc.n[cand];
-    const long long base = (long long)tile * TT;
-    const bool live = base < n;  // tiles past this candidate's end only contribute zeros
-    int* ctr = ws.tilectr + (long long)cand * ntiles + tile;
+    const int SP = S > 0 ? Smem::SP : ((Sx + 1) & ~1);
+    const int ngran = lc.ngran;
+    const int cpg = lc.gran / CH;  // chunks per granule
+    const int n = (int)lc.n[cand];
+    const int g0 = tb * gpb, g1 = min(g0 + gpb, ngran);
+    const int c_begin = g0 * cpg, c_end = min(g1 * cpg, (n + CH - 1) / CH);  // live chunks of this block
+    const int w = wb * THREADS + tid;
+    const bool active = w < W;
+    const long long cw = (long long)cand * W + w;
+    const double* __restrict__ gt = lc.t + (long long)cand * lc.npad;
+    const double* __restrict__ gterm = lc.term + (long long)cand * lc.npad;
 
     if (tid == 0) {
-        sm.doscan = 0;
-        if (live) {
-            mbar_init(&sm.mbar, 1);
-            mbar_expect_tx(&sm.mbar, 3u * TT * sizeof(double));
-            const long long g = (long long)cand * lc.npad + base;
-            tma_bulk_g2s(sm.t, lc.t + g, TT * sizeof(double), &sm.mbar);
-            tma_bulk_g2s(sm.f, lc.f + g, TT * sizeof(double), &sm.mbar);
-            tma_bulk_g2s(sm.w, lc.w + g, TT * sizeof(double), &sm.mbar);
+        trace_min(ws, 0);
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        if (c_begin < c_end) {
+            mbar_expect_tx(&sm.mbar[0], 2u * CH * sizeof(double));
+            tma_bulk_g2s(sm.traw[0], gt + (long long)c_begin * CH, CH * sizeof(double), &sm.mbar[0]);
+            tma_bulk_g2s(sm.term[0], gterm + (long long)c_begin * CH, CH * sizeof(double), &sm.mbar[0]);
         }
     }
     if (tid < Sx) sm.off[tid] = lc.off[(long long)cand * Sx + tid];
-    __syncthreads();
+    pdl_wait();  // everything above reads only the staged light curve; walkers come from the previous kernel
 
-    if (warp == NCW) {
-        // ------------------------------- producer ------------------------------------------
-        int pend_group[2] = {-1, -1};
-        for (int it = 0;; ++it) {
-            const int buf = it & 1;
-            if (it >= 2) {
-                bar_sync(BAR_EMPTY + buf, ALL);  // consumers finished group it-2: its warp sums are in smem
-                const int group = pend_group[buf];
-                const int nw_all = (W - group + ngroups - 1) / ngroups;
-                const int nw = nw_all < WT ? nw_all : WT;
-                if (lane < nw) {
-                    double sacc = 0.0;
-                    if (live) {
+    // per-walker constants (every block of the walker group derives them; the first one publishes
+    // what stage 2 and the finalisation need: proposal and model constants)
+    double vel = 0.0, nvtc = 0.0, b2 = 0.0;
+    int qhi = -1;  // padding lanes never hit
+    if (active) {
+        double par[6];
+        if (sc.enabled) {
+            const Proposal pr = propose_compute(sc, cand, w);
 #pragma unroll
-                        for (int i = 0; i < NCW; ++i) sacc += sm.warpsum[buf][lane][i];
-                    }
-                    ws.partials[((long long)cand * W + lane * ngroups + group) * ntiles + tile] = sacc;
-                }
-                __threadfence();
-                __syncwarp();
-                int tk = 0;
-                if (lane == 0) {
-                    int* gt = ws.grouptick + (long long)cand * ngroups + group;
-                    tk = atomicAdd(gt, 1);
-                    if (tk == ntiles - 1) *gt = 0;
-                }
-                tk = __shfl_sync(0xffffffffu, tk, 0);
-                if (tk == ntiles - 1) {  // last tile of this group: fold tiles, priors, settle
-                    __threadfence();
-                    if (lane < nw) {
-                        const long long cw = (long long)cand * W + lane * ngroups + group;
-                        const double* row = ws.partials + cw * ntiles;
-                        double sacc = 0.0;
-                        for (int i = 0; i < ntiles; ++i) sacc += __ldcg(row + i);
-                        const int n_w = __ldcg(ws.rhi + cw) - __ldcg(ws.rlo + cw);
-                        if (n_w <= 0) {  // never in transit: done here
-                            finish_walker(sc, cw, W, sacc, ws.lp[cw], lnprob, loglike);
-                            ws.rlo[cw] = INT_MAX;
-                            ws.rhi[cw] = 0;
-                        } else {
-                            ws.oot[cw] = sacc;
-                        }
-                    }
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int done = atomicAdd(ws.counters, 1);
-                        if (done == ngroups * (int)gridDim.z - 1) sm.doscan = 1;  // every group folded
-                    }
-                }
-                pend_group[buf] = -1;
-            }
-            int group = 0;
-            if (lane == 0) group = atomicAdd(ctr, 1);
-            group = __shfl_sync(0xffffffffu, group, 0);
-            const bool end = group >= ngroups;
-            if (!end) {
-                const int nw_all = (W - group + ngroups - 1) / ngroups;
-                const int nw = nw_all < WT ? nw_all : WT;
-                if (lane < WT) {
-                    if (live && lane < nw) {
-                        const WalkerConsts* wc = ws.wcs + ((long long)cand * W + lane * ngroups + group);
-                        sm.vel[buf][lane] = wc->vel; sm.nvtc[buf][lane] = wc->nvtc; sm.b2[buf][lane] = wc->b2;
-                        sm.qhi[buf][lane] = wc->qhi; sm.fbar[buf][lane] = wc->fbar;
-                    } else {  // padding walker: never in transit, result discarded
-                        sm.vel[buf][lane] = 0.0; sm.nvtc[buf][lane] = 0.0; sm.b2[buf][lane] = 0.0;
-                        sm.qhi[buf][lane] = -1; sm.fbar[buf][lane] = 1.0;
-                    }
-                }
-                pend_group[buf] = group;
-            }
-            if (lane == 0) sm.group[buf] = end ? -1 : group;
-            __syncwarp();
-            bar_arrive(BAR_FULL + buf, ALL);
-            if (end) {
-                // drain: the other buffer may still hold a group the consumers are working on
-                const int ob = buf ^ 1;
-                if (pend_group[ob] >= 0) {
-                    // reuse the loop body by running one more virtual iteration for that buffer
-                    bar_sync(BAR_EMPTY + ob, ALL);
-                    const int g2 = pend_group[ob];
-                    const int nw_all2 = (W - g2 + ngroups - 1) / ngroups;
-                    const int nw2 = nw_all2 < WT ? nw_all2 : WT;
-                    if (lane < nw2) {
-                        double sacc = 0.0;
-                        if (live) {
+            for (int d = 0; d < 6; ++d) par[d] = pr.q[d];
+            if (tb == 0) propose_store(sc, pr, cand, w, W);
+        } else {
 #pragma unroll
-                            for (int i = 0; i < NCW; ++i) sacc += sm.warpsum[ob][lane][i];
-                        }
-                        ws.partials[((long long)cand * W + lane * ngroups + g2) * ntiles + tile] = sacc;
-                    }
-                    __threadfence();
-                    __syncwarp();
-                    int tk = 0;
-                    if (lane == 0) {
-                        int* gt = ws.grouptick + (long long)cand * ngroups + g2;
-                        tk = atomicAdd(gt, 1);
-                        if (tk == ntiles - 1) *gt = 0;
-                    }
-                    tk = __shfl_sync(0xffffffffu, tk, 0);
-                    if (tk == ntiles - 1) {
-                        __threadfence();
-                        if (lane < nw2) {
-                            const long long cw = (long long)cand * W + lane * ngroups + g2;
-                            const double* row = ws.partials + cw * ntiles;
-                            double sacc = 0.0;
-                            for (int i = 0; i < ntiles; ++i) sacc += __ldcg(row + i);
-                            const int n_w = __ldcg(ws.rhi + cw) - __ldcg(ws.rlo + cw);
-                            if (n_w <= 0) {
-                                finish_walker(sc, cw, W, sacc, ws.lp[cw], lnprob, loglike);
-                                ws.rlo[cw] = INT_MAX;
-                                ws.rhi[cw] = 0;
-                            } else {
-                                ws.oot[cw] = sacc;
-                            }
-                        }
-                        __threadfence();
-                        __syncwarp();
-                        if (lane == 0) {
-                            const int done = atomicAdd(ws.counters, 1);
-                            if (done == ngroups * (int)gridDim.z - 1) sm.doscan = 1;
-                        }
-                    }
+            for (int d = 0; d < 6; ++d) par[d] = params[cw * 6 + d];
+        }
+        const WalkerConsts wc = make_walker_consts(par, Sx);
+        vel = wc.vel; nvtc = wc.nvtc; b2 = wc.b2; qhi = wc.qhi;
+        if (tb == 0) ws.wcs[cw] = wc;
+    }
+    __syncthreads();  // mbarrier init and offsets visible
+    if (tid == 0) trace_max(ws, 1);  // constants ready
+
+    double acc = 0.0;
+    int lo = INT_MAX, hi = 0;
+    double* __restrict__ prow = ws.partials + (long long)cand * ngran * W + w;
+    for (int c = c_begin; c < c_end; ++c) {
+        const int it = c - c_begin, buf = it & 1;
+        mbar_wait(&sm.mbar[buf], (it >> 1) & 1);
+        {   // fine-time table of this chunk
+            const double* tr = sm.traw[buf];
+            double* ft = sm.ftab[buf];
+            if (S > 0) {
+                for (int e = tid; e < CH * S; e += THREADS) {
+                    const int i = e / S, k = e - i * S;
+                    ft[i * SP + k] = tr[i] + sm.off[k];
                 }
-                break;
+            } else {
+                for (int e = tid; e < CH * Sx; e += THREADS) {
+                    const int i = e / Sx, k = e - i * Sx;
+                    ft[i * SP + k] = tr[i] + sm.off[k];
+                }
             }
         }
-    } else {
-        // ------------------------------- consumers -----------------------------------------
-        if (live) mbar_wait(&sm.mbar, 0);
-        for (int it = 0;; ++it) {
-            const int buf = it & 1;
-            bar_sync(BAR_FULL + buf, ALL);
-            const int group = sm.group[buf];
-            if (group < 0) break;
-            if (live) {
-                double acc[WT];
+        __syncthreads();  // table complete; every thread is past the previous chunk
+        if (tid == 0 && c + 1 < c_end) {
+            mbar_expect_tx(&sm.mbar[buf ^ 1], 2u * CH * sizeof(double));
+            tma_bulk_g2s(sm.traw[buf ^ 1], gt + (long long)(c + 1) * CH, CH * sizeof(double), &sm.mbar[buf ^ 1]);
+            tma_bulk_g2s(sm.term[buf ^ 1], gterm + (long long)(c + 1) * CH, CH * sizeof(double), &sm.mbar[buf ^ 1]);
+        }
+        const double* ft = sm.ftab[buf];
+        const double* tm = sm.term[buf];
+        const int base = c * CH;
+#pragma unroll 2
+        for (int i = 0; i < CH; ++i) {
+            const double* row = ft + i * SP;
+            int qmin = INT_MAX;
+            if (S > 0) {
 #pragma unroll
-                for (int wl = 0; wl < WT; ++wl) acc[wl] = 0.0;
-#pragma unroll 1
-                for (int s = 0; s < TPT; ++s) {
-                    const int li = s * CTHREADS + tid;
-                    const bool valid = (base + li) < n;
-                    const double ti = sm.t[li], fi = sm.f[li], wi = sm.w[li];
-                    const double r1 = fi - 1.0;
-                    const double term1 = wi * (r1 * r1);
-                    double ft[SR];
-                    if (S > 0) {
-#pragma unroll
-                        for (int k = 0; k < SR; ++k) ft[k] = ti + sm.off[k];
-                    }
-#pragma unroll
-                    for (int wl = 0; wl < WT; ++wl) {
-                        const double vel = sm.vel[buf][wl], nvtc = sm.nvtc[buf][wl], b2 = sm.b2[buf][wl];
-                        const int qhi = sm.qhi[buf][wl];
-                        int qmin = INT_MAX;  // smallest high word of q' over the S fine samples
-                        if (S > 0) {
-#pragma unroll
-                            for (int k = 0; k < SR; ++k) {
-                                const double vx = fma(vel, ft[k], nvtc);
-                                qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
-                            }
-                        } else {
-                            for (int k = 0; k < Sx; ++k) {
-                                const double vx = fma(vel, ti + sm.off[k], nvtc);
-                                qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
-                            }
-                        }
-                        const bool hit = (qmin <= qhi) && valid;
-                        const unsigned m = __ballot_sync(0xffffffffu, hit);
-                        if (m != 0 && lane == 0) {  // rare: this warp touches the transit of walker wl
-                            const long long cw = (long long)cand * W + wl * ngroups + group;
-                            const int w0i = (int)base + s * CTHREADS + warp * 32;
-                            atomicMin(ws.rlo + cw, w0i + (__ffs(m) - 1));
-                            atomicMax(ws.rhi + cw, w0i + (32 - __clz(m)));
-                        }
-                        const double fbar = sm.fbar[buf][wl];
-                        double term = term1;
-                        if (fbar != 1.0) {  // block-uniform, practically never taken
-                            const double r = fi - fbar;
-                            term = wi * (r * r);
-                        }
-                        acc[wl] += (valid && !hit) ? term : 0.0;
-                    }
+                for (int k = 0; k + 1 < S; k += 2) {
+                    const double2 f2 = *reinterpret_cast<const double2*>(row + k);
+                    const double vx0 = fma(vel, f2.x, nvtc), vx1 = fma(vel, f2.y, nvtc);
+                    qmin = min(qmin, min(__double2hiint(fma(vx0, vx0, b2)), __double2hiint(fma(vx1, vx1, b2))));
                 }
-#pragma unroll
-                for (int wl = 0; wl < WT; ++wl) {
-                    const double v = warp_sum(acc[wl]);
-                    if (lane == 0) sm.warpsum[buf][wl][warp] = v;
+                if (S & 1) {
+                    const double vx = fma(vel, row[S - 1], nvtc);
+                    qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
+                }
+            } else {
+                for (int k = 0; k < Sx; ++k) {
+                    const double vx = fma(vel, row[k], nvtc);
+                    qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
                 }
             }
-            __threadfence();  // range atomics of this group are visible before the producer's ticket
-            __syncwarp();
-            bar_arrive(BAR_EMPTY + buf, ALL);
+            const bool hit = qmin <= qhi;
+            const double term = tm[i];
+            if (!hit) acc += term;
+            if (hit) {
+                lo = min(lo, base + i);
+                hi = base + i + 1;
+            }
+        }
+        if ((c + 1) % cpg == 0 || c + 1 == c_end) {  // granule complete: publish its partial sum
+            if (active) prow[(long long)(c / cpg) * W] = acc;
+            acc = 0.0;
         }
     }
-    __syncthreads();
-    if (!sm.doscan) return;
+    pdl_trigger();  // stage 2 may be scheduled; it waits for this grid to finish before reading
+    {   // granules of this span that lie entirely beyond the light curve
+        const int gdone = (c_end > c_begin) ? (c_end + cpg - 1) / cpg : g0;
+        if (active)
+            for (int g = gdone; g < g1; ++g) prow[(long long)g * W] = 0.0;
+    }
+    if (active && hi > lo) {
+        atomicMin(ws.rlo + cw, lo);
+        atomicMax(ws.rhi + cw, min(hi, n));
+    }
+
+    // ---- last block of this walker group: fold granules in order, settle walkers that never transit
+    if (tid == 0) trace_max(ws, 2);  // sweep done
     __threadfence();
-    scan_items<ALL>(ws, W * (int)gridDim.z, item_ts, sm.s_scan);
-}
-
-// ---- per-walker setup for the brute-force sweep: constants + log-prior, one thread per walker ----
-__global__ void walker_setup_kernel(LcView lc, const double* __restrict__ params, int W,
-                                    const double* __restrict__ priors, EvalWs ws, SampleCtx sc) {
-    const int cw = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cw >= W * lc.ncand) return;
-    const int cand = cw / W;
-    const double* par = params;
-    if (sc.enabled) {
-        propose_stretch(sc, cand, cw % W, W);
-        par = sc.q;  // the proposal just written by this thread (not through the read-only path)
+    __syncthreads();
+    if (tid == 0) {
+        int* tk = ws.grouptick + (long long)cand * nwb + wb;
+        const int t = atomicAdd(tk, 1);
+        sm.flag = (t == ntb - 1);
+        if (sm.flag) *tk = 0;
     }
-    ws.wcs[cw] = make_walker_consts(par + (long long)cw * 6, lc.S);
-    ws.lp[cw] = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
+    __syncthreads();
+    if (!sm.flag) return;
+    __threadfence();
+    int lo_w = 0, hi_w = 0;
+    if (active) {
+        const double* col = ws.partials + (long long)cand * ngran * W + w;
+        double sacc = 0.0;
+        int g = 0;
+        for (; g + 16 <= ngran; g += 16) {  // sixteen loads in flight, summed in granule order
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __ldcg(col + (long long)(g + j) * W);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sacc += v[j];
+        }
+        for (; g < ngran; ++g) sacc += __ldcg(col + (long long)g * W);
+        lo_w = __ldcg(ws.rlo + cw);
+        hi_w = __ldcg(ws.rhi + cw);
+        if (hi_w - lo_w <= 0) {  // never in transit: done here
+            const double* par = (sc.enabled ? sc.q : params) + cw * 6;
+            const double lp = priors ? ln_prior_dev(par, priors + (long long)cand * 36, 6) : 0.0;
+            finish_walker(sc, cw, W, sacc, lp, lnprob, loglike);
+            ws.rlo[cw] = INT_MAX;
+            ws.rhi[cw] = 0;
+            lo_w = hi_w = 0;
+        } else {
+            ws.oot[cw] = sacc;
+        }
+    }
+    push_slots<THREADS>(ws, cw, lo_w, hi_w, sm.s_scan);
+    if (tid == 0) trace_max(ws, 3);  // fold + queue push done
 }
 
 // ---- windowed stage 1: one thread per walker ---------------------------------------------------
@@ -422,14 +362,16 @@ __device__ __forceinline__ int bsearch_t(const double* __restrict__ t, int n, do
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors,
-                     EvalWs ws, int item_ts, double* __restrict__ lnprob, double* __restrict__ loglike,
-                     SampleCtx sc) {
+                     EvalWs ws, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
     __shared__ int s_scan[THREADS / 32 + 1];
-    __shared__ int s_last;
     const int tid = threadIdx.x;
     const int CW = W * lc.ncand;
+    int lo_w = 0, hi_w = 0;
     const int cw = blockIdx.x * THREADS + tid;
     const int Sx = lc.S;
+    pdl_wait();     // walker positions come from the previous kernel
+    pdl_trigger();  // stage 2 may be scheduled; it waits for this grid to finish before reading
+    if (tid == 0) trace_min(ws, 0);
     if (cw < CW) {
         const int cand = cw / W;
         const int n = (int)lc.n[cand];
@@ -483,43 +425,39 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
         two_sum(sa, ph[ilo], sb, eb);
         eb += ea + pl[ilo];
         const double oot = sb + eb;
-        const double lp = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
-        if (ihi - ilo <= 0) {
+        if (ihi - ilo <= 0) {  // never in transit: done here
+            const double lp = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
             finish_walker(sc, cw, W, oot, lp, lnprob, loglike);
-            ws.rlo[cw] = INT_MAX;
-            ws.rhi[cw] = 0;
         } else {
             ws.oot[cw] = oot;
-            ws.lp[cw] = lp;
             ws.wcs[cw] = wc;
             ws.rlo[cw] = ilo;
             ws.rhi[cw] = ihi;
+            lo_w = ilo;
+            hi_w = ihi;
         }
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int done = atomicAdd(ws.counters, 1);
-        s_last = (done == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    scan_items<THREADS>(ws, CW, item_ts, s_scan);
+    push_slots<THREADS>(ws, cw, lo_w, hi_w, s_scan);
+    if (tid == 0) trace_max(ws, 3);
 }
 
 // ---- stage 2: evaluate the in-transit ranges -------------------------------------------------
-// Each WARP pulls (walker, chunk) items on its own (no block barriers): it walks the chunk in
-// groups of TSW timestamps, one supersample per lane and round, parks the fluxes in its private
-// shared-memory scratch, lets the first TSW lanes reduce the bins and accumulate residuals, and
-// publishes the item's partial sum; the warp that completes a walker's last item folds the items
-// (fixed order), adds the priors and writes lnprob.
-constexpr int kMaxTSW = 32;
+// The queue of slots is split evenly and statically over all resident warps (no work-fetching
+// atomics).  A warp walks its slots pass by pass: one supersample per lane and round, fluxes parked
+// in its private shared-memory scratch, bins reduced in NumPy's order by one lane per timestamp,
+// residuals accumulated; each slot's partial is stored.  When the warp leaves a walker it reports
+// how many of the walker's slots it finished; the warp that completes the walker folds the slot
+// partials in slot order, evaluates the priors (one parameter per lane) and writes lnprob or runs
+// the sampler's accept step.
+#ifndef NMB_EVALPASS
+#define NMB_EVALPASS 96
+#endif
+constexpr int kEvalPass = NMB_EVALPASS;  // supersamples a warp evaluates per pass
 
 // PATH: 0 = general IEEE FP64, 1 = FP64 hot path (default), 2 = FP32 hot path (NMB_F32)
 template <int PATH>
 __device__ __forceinline__ double sample_flux_eval(double ti, double offk, const WalkerConsts& wc,
-                                                   const QuadConstsF& cf);
+                                                   const QuadConstsF& cf, const QuadConsts* gq);
 
 __device__ __noinline__ double sample_flux_slowpath(double z, const QuadConsts* q) {
     return occultquad_point<false, IeeeOps>(z, *q, nullptr, nullptr, nullptr);
@@ -527,7 +465,7 @@ __device__ __noinline__ double sample_flux_slowpath(double z, const QuadConsts* 
 
 template <>
 __device__ __forceinline__ double sample_flux_eval<1>(double ti, double offk, const WalkerConsts& wc,
-                                                      const QuadConstsF&) {
+                                                      const QuadConstsF&, const QuadConsts* gq) {
     const double ft = ti + offk;
     const double x = ft - wc.tcen;
     const double vx = wc.vel * x;
@@ -539,18 +477,18 @@ __device__ __forceinline__ double sample_flux_eval<1>(double ti, double offk, co
     // operands outside the normal range -> non-finite z or F) takes the general IEEE path
     if (!occultquad_hot(z, wc.q, F) || !(fabs(F) <= 1e300)) {
         const double zz = ::sqrt(q);
-        F = (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, &wc.q);
+        F = (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, gq);
     }
     return F;
 }
 template <>
 __device__ __forceinline__ double sample_flux_eval<0>(double ti, double offk, const WalkerConsts& wc,
-                                                      const QuadConstsF&) {
+                                                      const QuadConstsF&, const QuadConsts*) {
     return sample_flux(ti, offk, wc);
 }
 template <>
 __device__ __forceinline__ double sample_flux_eval<2>(double ti, double offk, const WalkerConsts& wc,
-                                                      const QuadConstsF& cf) {
+                                                      const QuadConstsF& cf, const QuadConsts* gq) {
     const double ft = ti + offk;
     const double x = ft - wc.tcen;          // FP64 difference of the absolute times, then FP32
     const float vx = (float)wc.vel * (float)x;
@@ -561,121 +499,149 @@ __device__ __forceinline__ double sample_flux_eval<2>(double ti, double offk, co
     // anything else (other cases, exact limb, non-finite): the FP64 general path
     const double vxd = wc.vel * x;
     const double zz = ::sqrt(wc.b2 + vxd * vxd);
-    return (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, &wc.q);
+    return (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, gq);
 }
 
-template <int S, int THREADS>
+template <int THREADS>
 struct EvalSmem {
-    double scratch[THREADS / 32][kMaxTSW * ((S > 0 ? S : kMaxS) | 1)];
+    // per warp: TSW bins of S fluxes at an odd stride; TSW * S <= kEvalPass
+    double scratch[THREADS / 32][2 * kEvalPass + 8];
+    // the current walker's constants, one copy per warp: operands come from shared memory when
+    // needed instead of pinning ~40 registers for the whole pass
+    WalkerConsts wc[THREADS / 32];
 };
-
-struct ItemMeta {
-    int cw, first, nch, lo, hi;
-};
-__device__ __forceinline__ ItemMeta load_item_meta(const EvalWs& ws, int item, int total) {
-    ItemMeta m;
-    m.cw = -1; m.first = 0; m.nch = 1; m.lo = 0; m.hi = 0;
-    if (item < total) {
-        m.cw = __ldg(ws.itemwalker + item);
-        m.first = __ldcg(ws.blkstart + m.cw);
-        m.nch = __ldcg(ws.blkstart + m.cw + 1) - m.first;
-        m.lo = __ldcg(ws.rlo + m.cw);
-        m.hi = __ldcg(ws.rhi + m.cw);
-    }
-    return m;
-}
 
 template <int S, int THREADS, int MINB, int PATH>
 __global__ void __launch_bounds__(THREADS, MINB)
-eval_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
-                   int TSW, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
+eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
+                  int nsm, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
     constexpr int NWARP = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    EvalSmem<S, THREADS>& sm = *reinterpret_cast<EvalSmem<S, THREADS>*>(smem_raw);
+    EvalSmem<THREADS>& sm = *reinterpret_cast<EvalSmem<THREADS>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Sx = s_of<S>(lc.S);
     const int SP = Sx | 1;
-    const int total = ws.counters[1];
+    const int TSW = ws.tsw;
+    pdl_wait();  // stage 1 complete, its queue visible
+    const int total = __ldcg(ws.counters + 1);
     double* scratch = sm.scratch[warp];
-    // stage 1 is complete: rearm its per-tile group queues for the next launch
-    for (int i = blockIdx.x * THREADS + threadIdx.x; i < ws.ntilectr; i += gridDim.x * THREADS) ws.tilectr[i] = 0;
+    if (threadIdx.x == 0) trace_min(ws, 8);
 
-    // dynamic item queue, software pipelined: the index two items ahead is being fetched and the
-    // metadata of the next item is in flight while the current item is evaluated
+    // warp index that runs over SMs first, then sub-partitions, then resident blocks of an SM
+    // (blocks b, b + nsm, ... share an SM in a one-wave launch), so a short queue still touches
+    // every sub-partition of the GPU
+    const int nwarps = gridDim.x * NWARP;
+    const int gw = (((int)blockIdx.x / nsm) * NWARP + warp) * nsm + (int)blockIdx.x % nsm;
+    // chunks of slots: the first chunk of a warp is its own index (no atomic on the way to the first
+    // sample), further chunks come from a shared counter, fetched one chunk ahead
+    const int chunk = max(1, total / (nwarps * 4));
+    const int nchunks = (total + chunk - 1) / chunk;
     int* queue = ws.counters + 2;
-    int idx_cur = 0, idx_nxt = 0;
-    if (lane == 0) {
-        idx_cur = atomicAdd(queue, 1);
-        idx_nxt = atomicAdd(queue, 1);
+    int ch_cur = gw, ch_nxt = INT_MAX;
+    if (nchunks > nwarps) {
+        if (lane == 0) ch_nxt = nwarps + atomicAdd(queue, 1);
+        ch_nxt = __shfl_sync(0xffffffffu, ch_nxt, 0);
     }
-    idx_cur = __shfl_sync(0xffffffffu, idx_cur, 0);
-    idx_nxt = __shfl_sync(0xffffffffu, idx_nxt, 0);
-    ItemMeta nxt = load_item_meta(ws, idx_cur, total);
-    while (idx_cur < total) {
-        const int item = idx_cur;
-        const ItemMeta cur = nxt;
-        int idx_nn = 0;
-        if (lane == 0) idx_nn = atomicAdd(queue, 1);
-        nxt = load_item_meta(ws, idx_nxt, total);
-        const int cw = cur.cw;
-        const int cand = cw / W;
-        const WalkerConsts wc = ws.wcs[cw];
-        const QuadConstsF cf = (PATH == 2) ? to_f32(wc.q) : QuadConstsF{};
-        const int ci = item - cur.first;
-        const int n_w = cur.hi - cur.lo;
-        int clen = (n_w + cur.nch - 1) / cur.nch;
-        clen = (clen + TSW - 1) / TSW * TSW;
-        const int cstart = cur.lo + ci * clen;
-        const int cend = min(cur.hi, cstart + clen);
-        const double* __restrict__ gt = lc.t + (long long)cand * lc.npad;
-        const double* __restrict__ gf = lc.f + (long long)cand * lc.npad;
-        const double* __restrict__ gw = lc.w + (long long)cand * lc.npad;
-        const double* __restrict__ goff = lc.off + (long long)cand * Sx;
 
+    int cur_cw = -1, cur_first = 0, seg = 0, cand = 0;
+    WalkerConsts& wc = sm.wc[warp];
+    QuadConstsF cf = QuadConstsF{};
+    const double *gt = nullptr, *gf = nullptr, *gw_ = nullptr, *goff = nullptr;
+    SlotRec rec{}, nxt{};
+    if (lane == 0) trace_max(ws, 9);
+    while (ch_cur < nchunks) {
+      const int s0 = ch_cur * chunk, s1 = min(total, s0 + chunk);
+      int ch_nn = INT_MAX;
+      if (lane == 0 && ch_nxt < nchunks) ch_nn = nwarps + atomicAdd(queue, 1);
+      *reinterpret_cast<int4*>(&nxt) = __ldcg(reinterpret_cast<const int4*>(ws.slots + s0));
+      for (int s = s0; s <= s1; ++s) {
+        const bool last = (s == s1);
+        rec = nxt;
+        if (s + 1 < s1) *reinterpret_cast<int4*>(&nxt) = __ldcg(reinterpret_cast<const int4*>(ws.slots + s + 1));
+        if (cur_cw >= 0 && (last || rec.cw != cur_cw)) {
+            // leaving walker cur_cw: report `seg` finished slots; the warp that completes it finishes it
+            int done = 0;
+            const int nsl = __ldcg(ws.nslots + cur_cw);
+            if (lane == 0 && seg < nsl) {
+                __threadfence();
+                done = atomicAdd(ws.slotsdone + cur_cw, seg);
+            }
+            done = __shfl_sync(0xffffffffu, done, 0);
+            if (done + seg == nsl) {
+                if (seg < nsl) __threadfence();
+                __syncwarp();
+                const double* part = ws.slotpart + cur_first;
+                double ssum = 0.0;
+                for (int c = lane; c < nsl; c += 32) ssum += __ldcg(part + c);
+                ssum = warp_sum(ssum);
+                const double* par = (sc.enabled ? sc.q : params) + (long long)cur_cw * 6;
+                const double lp = priors ? ln_prior_warp(par, priors + (long long)(cur_cw / W) * 36, 6, lane) : 0.0;
+                if (lane == 0) {
+                    finish_walker(sc, cur_cw, W, ws.oot[cur_cw] + ssum, lp, lnprob, loglike);
+                    ws.slotsdone[cur_cw] = 0;
+                    ws.rlo[cur_cw] = INT_MAX;
+                    ws.rhi[cur_cw] = 0;
+                }
+            }
+        }
+        if (last) break;
+        if (rec.cw != cur_cw) {
+            cur_cw = rec.cw;
+            cur_first = rec.first;
+            seg = 0;
+            cand = cur_cw / W;
+            {
+                static_assert(sizeof(WalkerConsts) % 8 == 0, "WalkerConsts is copied as doubles");
+                const double* src = reinterpret_cast<const double*>(ws.wcs + cur_cw);
+                double* dst = reinterpret_cast<double*>(&wc);
+                __syncwarp();
+                for (int i = lane; i < (int)(sizeof(WalkerConsts) / 8); i += 32) dst[i] = __ldcg(src + i);
+                __syncwarp();
+            }
+            if (PATH == 2) cf = to_f32(wc.q);
+            gt = lc.t + (long long)cand * lc.npad;
+            gf = lc.f + (long long)cand * lc.npad;
+            gw_ = lc.w + (long long)cand * lc.npad;
+            goff = lc.off + (long long)cand * Sx;
+        }
         double acc = 0.0;
-        for (int sub = cstart; sub < cend; sub += TSW) {
-            const int nts = min(TSW, cend - sub);
+        for (int sub = rec.t0; sub < rec.t1; sub += TSW) {
+            const int nts = min(TSW, rec.t1 - sub);
             const int nsamp = nts * Sx;
             for (int j = lane; j < nsamp; j += 32) {
                 const int h = j / Sx, k = j - h * Sx;
-                scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + sub + h), __ldg(goff + k), wc, cf);
+                scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + sub + h), __ldg(goff + k), wc, cf, &ws.wcs[cur_cw].q);
             }
             __syncwarp();
-            if (lane < nts) {
-                const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + lane * SP)
-                                         : bin_mean_rt(scratch + lane * SP, Sx);
-                const double r = __ldg(gf + sub + lane) - m;
-                acc += __ldg(gw + sub + lane) * (r * r);
+            for (int h = lane; h < nts; h += 32) {
+                const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + h * SP)
+                                         : bin_mean_rt(scratch + h * SP, Sx);
+                const double r = __ldg(gf + sub + h) - m;
+                acc += __ldg(gw_ + sub + h) * (r * r);
             }
             __syncwarp();
         }
         acc = warp_sum(acc);
-        bool fold = (cur.nch == 1);
-        double s = acc;
-        if (!fold) {  // several items per walker: publish, and let the last one fold them in order
-            int done = 0;
-            if (lane == 0) {
-                ws.itempart[item] = acc;
-                __threadfence();
-                done = atomicAdd(ws.itemsdone + cw, 1);
-            }
-            done = __shfl_sync(0xffffffffu, done, 0);
-            if (done == cur.nch - 1) {
-                __threadfence();
-                s = 0.0;
-                for (int c = lane; c < cur.nch; c += 32) s += __ldcg(ws.itempart + cur.first + c);
-                s = warp_sum(s);
-                fold = true;
-            }
+        if (lane == 0) ws.slotpart[s] = acc;
+        ++seg;
+        if (lane == 0) trace_max(ws, 10);  // slot evaluated
+      }
+      cur_cw = -1;
+      ch_cur = ch_nxt;
+      ch_nxt = __shfl_sync(0xffffffffu, ch_nn, 0);
+    }
+    if (lane == 0) trace_max(ws, 11);  // warp done
+    pdl_trigger();
+    // the last block to finish re-arms the queue counters for the next evaluation
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(ws.counters + 3, 1);
+        if (done == (int)gridDim.x - 1) {
+            ws.counters[1] = 0;
+            ws.counters[2] = 0;
+            ws.counters[3] = 0;
         }
-        if (fold && lane == 0) {
-            finish_walker(sc, cw, W, ws.oot[cw] + s, ws.lp[cw], lnprob, loglike);
-            ws.itemsdone[cw] = 0;
-            ws.rlo[cw] = INT_MAX;
-            ws.rhi[cw] = 0;
-        }
-        idx_cur = idx_nxt;
-        idx_nxt = __shfl_sync(0xffffffffu, idx_nn, 0);
     }
 }
 

@@ -26,6 +26,7 @@ struct LcView {
     const double* t;       // [C][npad]
     const double* f;       // [C][npad]
     const double* w;       // [C][npad]   -2 * err**-2            (namaste.py:1347)
+    const double* term;    // [C][npad]   w * (f - 1)^2: chi^2 term of a timestamp whose model is exactly 1
     const double* pre_hi;  // [C][npad+1] prefix sum of w*(f-1)^2, high word
     const double* pre_lo;  // [C][npad+1] low word (double-double)
     const double* off;     // [C][S]      cad * (k * (1/S))        (namaste.py:1159)
@@ -37,6 +38,8 @@ struct LcView {
     const int* gcount;     // [C]  last valid j
     long long gstride;
     long long npad;
+    int gran;              // timestamps per reduction granule (power of two, fixed per staged batch)
+    int ngran;             // npad / gran
     int ncand;
     int S;
 };
@@ -117,6 +120,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
             : "memory");
     } while (!ok);
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; pdl_wait() blocks until
+// the predecessor has completed and its writes are visible (no-op without the attribute), and
+// pdl_trigger() tells the scheduler that this block no longer needs to hold the successor back.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -56,8 +56,14 @@ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
     return (double)x * 1.1102230246251565e-16;  // 2^-53, in [0, 1)
 }
 
-// Proposal for evaluated walker `k` (index within this launch) of candidate `cand`.
-__device__ __forceinline__ void propose_stretch(const SampleCtx& sc, int cand, int k, int Weval) {
+// Proposal for evaluated walker `k` (index within this launch) of candidate `cand`: a pure function
+// of (seed, step, half, candidate, walker) and the current positions, so several thread blocks may
+// recompute it; exactly one of them stores it (propose_store).
+struct Proposal {
+    double q[6];
+    double zz, u_a;
+};
+__device__ __forceinline__ Proposal propose_compute(const SampleCtx& sc, int cand, int k) {
     const int halfk = sc.W / 2;
     const int nS0 = sc.half == 0 ? halfk : sc.W - halfk;
     const int nS1 = sc.W - nS0;
@@ -69,17 +75,28 @@ __device__ __forceinline__ void propose_stretch(const SampleCtx& sc, int cand, i
                   (uint32_t)sc.seed, (uint32_t)(sc.seed >> 32), r);
     philox4x32_10((uint32_t)sc.step, (uint32_t)(sc.step >> 32), (walker << 1) | (uint32_t)sc.half, (cnd << 1) | 1u,
                   (uint32_t)sc.seed, (uint32_t)(sc.seed >> 32), r2);
-    const double u_z = u01_53(r[0], r[1]), u_j = u01_53(r[2], r[3]), u_a = u01_53(r2[0], r2[1]);
+    const double u_z = u01_53(r[0], r[1]), u_j = u01_53(r[2], r[3]);
+    Proposal pr;
+    pr.u_a = u01_53(r2[0], r2[1]);
     const double t = (sc.a - 1.) * u_z + 1;
-    const double zz = t * t / sc.a;
+    pr.zz = t * t / sc.a;
     int j = (int)(u_j * (double)nS1);
     if (j >= nS1) j = nS1 - 1;
     const double* s = sc.pos + ((long long)cand * sc.W + i) * sc.ndim;
     const double* c = sc.pos + ((long long)cand * sc.W + c_base + j) * sc.ndim;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) pr.q[d] = c[d] - pr.zz * (c[d] - s[d]);
+    return pr;
+}
+__device__ __forceinline__ void propose_store(const SampleCtx& sc, const Proposal& pr, int cand, int k, int Weval) {
     const long long e = (long long)cand * Weval + k;
-    for (int d = 0; d < sc.ndim; ++d) sc.q[e * sc.ndim + d] = c[d] - zz * (c[d] - s[d]);
-    sc.zz[e] = zz;
-    sc.logu[e] = log(u_a);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) sc.q[e * 6 + d] = pr.q[d];
+    sc.zz[e] = pr.zz;
+    sc.logu[e] = log(pr.u_a);
+}
+__device__ __forceinline__ void propose_stretch(const SampleCtx& sc, int cand, int k, int Weval) {
+    propose_store(sc, propose_compute(sc, cand, k), cand, k, Weval);
 }
 
 // Accept/reject + chain append for evaluated walker `k`; newlnp = loglike + lnprior of its proposal.
