@@ -78,11 +78,12 @@ def make_workload(name, seed_offset=0):
 
 
 def count_samples(wl):
-    """Per-ensemble counts of fine samples: total, interior (planet inside the disc) and
-    ingress/egress, for the FLOP formula of SURVEY.md 8(d)."""
+    """Per-ensemble counts for the FLOP formula of SURVEY.md 8(d): fine samples in total, interior
+    (planet inside the disc) and ingress/egress samples, and timestamps with at least one
+    in-transit sample (those are evaluated by stage 2, the others by stage 1 alone)."""
     t, S, cad = wl["lc"][:, 0], wl["S"], wl["cad"]
     off = cad * np.arange(0, 1.0, 1 / S)
-    m_int = m_edge = 0
+    m_int = m_edge = t_in = 0
     for par in wl["pos"]:
         tcen, b, vel, rp = par[0], par[1], par[2], abs(par[3])
         h2 = (1 + rp) ** 2 - b * b
@@ -95,17 +96,26 @@ def count_samples(wl):
             sel = np.where(np.abs(t - tcen) < half)[0]
         if len(sel) == 0:
             continue
-        ft = (t[sel, None] + off[None, :]).ravel()
-        z = np.sqrt(b * b + (vel * (ft - tcen)) ** 2)
+        z = np.sqrt(b * b + (vel * ((t[sel, None] + off[None, :]) - tcen)) ** 2)
         inner = z < abs(1 - rp)
+        limb = (z < 1 + rp) & ~inner
         m_int += int(np.sum(inner))
-        m_edge += int(np.sum((z < 1 + rp) & ~inner))
-    return wl["W"] * wl["N"] * S, m_int, m_edge
+        m_edge += int(np.sum(limb))
+        t_in += int(np.sum(np.any(inner | limb, axis=1)))
+    return wl["W"] * wl["N"] * S, m_int, m_edge, t_in
 
 
 def algorithmic_flops(wl):
-    m, m_int, m_edge = count_samples(wl)
-    return m * 7 + m_int * 143 + m_edge * 180 + wl["W"] * wl["N"] * 5 + wl["W"] * 40, (m, m_int, m_edge)
+    """7 per fine sample + 143 per interior + 180 per ingress/egress sample + 5 per
+    timestamp + 40 per walker, split between the two kernels of the brute-force pipeline: the sweep
+    visits every fine sample and closes the out-of-transit timestamps, stage 2 adds the in-transit
+    terms, the residuals of the in-transit timestamps and the priors (its recomputation of z for
+    those samples is implementation work and is not counted)."""
+    m, m_int, m_edge, t_in = count_samples(wl)
+    wn = wl["W"] * wl["N"]
+    sweep = m * 7 + (wn - t_in) * 5
+    evalk = m_int * 143 + m_edge * 180 + t_in * 5 + wl["W"] * 40
+    return sweep + evalk, sweep, evalk, (m, m_int, m_edge, t_in)
 
 
 # --------------------------------------------------------------------------------------------
@@ -293,6 +303,11 @@ def run_ours(args):
         torch.cuda.synchronize()
     clk = clocks.stop(t_b, time.perf_counter())
     ms_brute = max_over_ranks(ms_brute)
+    # per-kernel durations of the same loop (CUDA events between the two kernels of every step)
+    staged.stage_timing(True)
+    device_loop("brute", args.steps)
+    ms_s1, ms_s2, _ = staged.stage_times()
+    staged.stage_timing(False)
     device_loop("windowed", max(args.warmup, 3))
     ms_win, _, _ = device_loop("windowed", args.steps)
     ms_win = max_over_ranks(ms_win)
@@ -358,16 +373,23 @@ def run_ours(args):
 
     units = W * N * world
     value = units / (ms_brute / args.steps * 1e-3)
-    flops, (m, m_int, m_edge) = algorithmic_flops(wl)
+    flops, fl_sweep, fl_eval, (m, m_int, m_edge, t_in) = algorithmic_flops(wl)
     peak_tf, _ = nb.measure_fp64_peak()
-    achieved_tf = flops / (ms_brute / args.steps * 1e-3) / 1e12
-    traffic = None
+    step_s = ms_brute / args.steps * 1e-3
+    traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            traffic = json.load(open(tpath)).get(args.workload) or {}
         except Exception:
-            traffic = None
+            traffic = {}
+    kernels = []
+    for name, ms, fl in (("sweep_walkers_kernel", ms_s1, fl_sweep), ("eval_slots_kernel", ms_s2, fl_eval)):
+        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        kernels.append({"kernel": name, "ms_per_launch": ms,
+                        "share_of_step": ms / (ms_s1 + ms_s2) if ms_s1 + ms_s2 > 0 else None,
+                        "flops_per_launch": fl, "achieved": tf, "frac": tf / peak_tf, "traffic": traffic.get(name)})
+    dom = max(kernels, key=lambda k: k["ms_per_launch"])
     line = {
         "metric": "lnprob_walker_timestamp_evals_per_sec", "value": value, "unit": "wt/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_brute / args.steps,
@@ -391,12 +413,16 @@ def run_ours(args):
         "fp32": {"value": units / (ms_f32 / args.steps * 1e-3), "unit": "wt/s", "ms_per_step": ms_f32 / args.steps,
                  "max_rel_err_vs_fp64": f32_err,
                  "note": "NMB_F32: FP32 transit model (depth space) in the windowed pipeline; reported separately"},
-        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": traffic,
+        "roofline": {"bound": "fp64", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": dom["frac"], "traffic": dom["traffic"],
                      "peak_source": "DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 entry)",
-                     "flops_per_launch": flops,
                      "flops_convention": "SURVEY.md 8(d): 7/fine sample + 143 interior + 180 ingress + 5/timestamp + 40/walker",
-                     "fine_samples": m, "interior": m_int, "edge": m_edge},
+                     "fine_samples": m, "interior": m_int, "edge": m_edge, "in_transit_timestamps": t_in,
+                     "kernels": kernels,
+                     "whole_step": {"flops": flops, "ms": ms_brute / args.steps, "achieved": flops / step_s / 1e12,
+                                    "frac": flops / step_s / 1e12 / peak_tf},
+                     "note": "dominant kernel = the longer of the two launches of a brute-force step; per-kernel "
+                             "durations from CUDA events between the kernels (they do not overlap while measured)"},
     }
     if world == 1 and not args.no_cpu and not args.profile:
         import multiprocessing as mp

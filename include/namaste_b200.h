@@ -128,6 +128,10 @@ void* nmb_sampler_stream(nmb_sampler* s);
 /* ---- measurement helpers (used by bench.py) ------------------------------------------------ */
 /* Sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), CUDA-event timed. */
 int nmb_measure_fp64_peak(double* tflops, double* ms);
+/* per-kernel device timing of the two pipeline stages (CUDA events on the launching stream):
+ * enable, run evaluations, then read the mean stage-1 / stage-2 kernel durations in ms (and reset) */
+int nmb_stage_timing(nmb_lc* lc, int enable);
+int nmb_stage_times(nmb_lc* lc, double* stage1_ms, double* stage2_ms, int64_t* count);
 /* diagnostics: phase envelopes (globaltimer ns) of the last evaluation; needs NMB_TRACE=1 in the environment */
 int nmb_debug_trace(nmb_lc* lc, uint64_t* out16);
 /* number of kernels this library has launched so far in this process */

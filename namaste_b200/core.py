@@ -129,6 +129,16 @@ class LightCurve:
                              ctypes.c_void_p(stream)), "lnprob_device")
         return out
 
+    def stage_timing(self, enable=True):
+        """Switch per-kernel device timing of the two pipeline stages on or off (resets the means)."""
+        check(load().nmb_stage_timing(self._h, 1 if enable else 0), "stage_timing")
+
+    def stage_times(self):
+        """(stage-1 ms, stage-2 ms, evaluations) averaged since the last call; needs stage_timing()."""
+        a, b, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        check(load().nmb_stage_times(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)), "stage_times")
+        return a.value, b.value, int(n.value)
+
     def model(self, params, cand=0):
         """MonotransitModel.get_value for W parameter rows -> [W, N] (host arrays)."""
         import torch

@@ -37,6 +37,44 @@ constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-t
 
 }  // namespace
 
+// Per-stage device timing (nmb_stage_timing / nmb_stage_times): CUDA events around stage 1 and
+// stage 2 of every evaluation on the launching stream.  The event between the two kernels keeps
+// them from overlapping, so these are per-kernel durations, not a decomposition of the step time.
+struct StageTimer {
+    bool on = false;
+    static constexpr int kRing = 64;
+    cudaEvent_t e[kRing][3] = {};
+    int head = 0, pending = 0;
+    double acc1 = 0, acc2 = 0;
+    long n = 0;
+    void enable(bool v) {
+        if (v && !e[0][0])
+            for (auto& r : e) for (auto& x : r) cudaEventCreate(&x);
+        on = v;
+    }
+    void mark(int i, cudaStream_t st) { if (on) cudaEventRecord(e[head][i], st); }
+    void drain(int keep) {
+        while (pending > keep) {
+            const int idx = (head - pending + 2 * kRing) % kRing;
+            cudaEventSynchronize(e[idx][2]);
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, e[idx][0], e[idx][1]);
+            cudaEventElapsedTime(&b, e[idx][1], e[idx][2]);
+            acc1 += a; acc2 += b; ++n;
+            --pending;
+        }
+    }
+    void done() {
+        if (!on) return;
+        head = (head + 1) % kRing;
+        ++pending;
+        drain(kRing - 1);
+    }
+    ~StageTimer() {
+        if (e[0][0]) for (auto& r : e) for (auto& x : r) cudaEventDestroy(x);
+    }
+};
+
 struct nmb_lc {
     int64_t ncand = 0, nmax = 0, npad = 0;
     int S = 0;
@@ -60,6 +98,7 @@ struct nmb_lc {
     double *h_pin = nullptr, *d_stage = nullptr;
     size_t pin_cap = 0, stage_cap = 0;
     cudaStream_t own_stream = nullptr;
+    StageTimer timer;
 
     nmb::LcView view() const {
         nmb::LcView v;
@@ -267,32 +306,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
-// NMB_STAGE_TIMING=1: time stage 1 / stage 2 separately with CUDA events (diagnostics only)
-struct StageTimer {
-    bool on = false;
-    cudaEvent_t e[3];
-    double acc1 = 0, acc2 = 0;
-    long n = 0;
-    StageTimer() {
-        on = std::getenv("NMB_STAGE_TIMING") != nullptr;
-        if (on) for (auto& x : e) cudaEventCreate(&x);
-    }
-    void mark(int i, cudaStream_t st) { if (on) cudaEventRecord(e[i], st); }
-    void done(const char* what) {
-        if (!on) return;
-        cudaEventSynchronize(e[2]);
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, e[0], e[1]);
-        cudaEventElapsedTime(&b, e[1], e[2]);
-        acc1 += a; acc2 += b; ++n;
-        if (n % 100 == 0) {
-            fprintf(stderr, "[nmb stage timing] %s: stage1 %.2f us, stage2 %.2f us (mean of 100)\n", what,
-                    1e3 * acc1 / 100, 1e3 * acc2 / 100);
-            acc1 = acc2 = 0;
-        }
-    }
-};
-StageTimer g_timer;
+
 
 int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
     nmb::EvalWs& ws = lc->ws;
@@ -400,7 +414,7 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, lc->ngran, st)) return rc;
-    g_timer.mark(0, st);
+    lc->timer.mark(0, st);
     // 128-walker blocks when they alone fill the GPU, single-warp blocks (finer spread) otherwise
     static const int force_thr = std::getenv("NMB_SWEEP_THREADS") ? std::atoi(std::getenv("NMB_SWEEP_THREADS")) : 0;
     const long long blocks128 = (long long)lc->ncand * ((W + 127) / 128) * lc->ngran;
@@ -408,10 +422,10 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     int rc = wide ? launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc)
                   : launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (rc) return rc;
-    g_timer.mark(1, st);
+    lc->timer.mark(1, st);
     rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
-    g_timer.mark(2, st);
-    g_timer.done("brute");
+    lc->timer.mark(2, st);
+    lc->timer.done();
     return rc;
 }
 
@@ -421,14 +435,14 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
     constexpr int kWinThreads = 64;
-    g_timer.mark(0, st);
+    lc->timer.mark(0, st);
     CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),
                   dim3(kWinThreads), 0, st, lc->view(), params, W, priors, lc->ws, lnprob, loglike, sc));
     g_launches++;
-    g_timer.mark(1, st);
+    lc->timer.mark(1, st);
     const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
-    g_timer.mark(2, st);
-    g_timer.done("windowed");
+    lc->timer.mark(2, st);
+    lc->timer.done();
     return rc;
 }
 
@@ -590,6 +604,25 @@ extern "C" int nmb_debug_trace(nmb_lc* lc, uint64_t* out) {
     uint64_t init[16] = {0};
     init[0] = init[8] = ~0ull;
     CU(cudaMemcpy(lc->ws.trace, init, sizeof init, cudaMemcpyHostToDevice));
+    return NMB_OK;
+}
+
+extern "C" int nmb_stage_timing(nmb_lc* lc, int enable) {
+    if (!lc) return fail(NMB_ERR_ARG, "nmb_stage_timing: null pointer");
+    lc->timer.drain(0);
+    lc->timer.acc1 = lc->timer.acc2 = 0; lc->timer.n = 0;
+    lc->timer.enable(enable != 0);
+    return NMB_OK;
+}
+
+extern "C" int nmb_stage_times(nmb_lc* lc, double* stage1_ms, double* stage2_ms, int64_t* count) {
+    if (!lc || !stage1_ms || !stage2_ms) return fail(NMB_ERR_ARG, "nmb_stage_times: null pointer");
+    lc->timer.drain(0);
+    const long n = lc->timer.n;
+    *stage1_ms = n ? lc->timer.acc1 / n : 0.0;
+    *stage2_ms = n ? lc->timer.acc2 / n : 0.0;
+    if (count) *count = n;
+    lc->timer.acc1 = lc->timer.acc2 = 0; lc->timer.n = 0;
     return NMB_OK;
 }
 

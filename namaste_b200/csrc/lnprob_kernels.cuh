@@ -90,7 +90,10 @@ __device__ __forceinline__ WalkerConsts make_walker_consts(const double* par, in
     w.qthr_c = (w.q.p == 0.0) ? -1.0 : u * u * (1.0 + 8 * kEps);
     // q' >= 0 for finite inputs, so its IEEE bit pattern orders like an integer
     const bool finite = (fabs(w.vel) <= 1e300) && (fabs(vtc) <= 1e300) && (w.b2 <= 1e300) && (w.qthr_c <= 1e300);
-    w.qhi = !finite ? INT_MAX : (w.qthr_c < 0.0 ? -1 : __double2hiint(w.qthr_c));
+    // the sweep adds the precomputed term w*(f-1)^2 for out-of-transit timestamps, which assumes an
+    // out-of-transit model of exactly 1; if the limb-darkening normalisation is degenerate
+    // (fout != 1, e.g. 1 - LD1/3 - LD2/6 == 0 or non-finite coefficients) every sample goes to stage 2
+    w.qhi = (!finite || !(w.fbar == 1.0)) ? INT_MAX : (w.qthr_c < 0.0 ? -1 : __double2hiint(w.qthr_c));
     w.pad_ = 0;
     return w;
 }

@@ -8,6 +8,10 @@ Namaste user can switch imports; all arithmetic runs in the CUDA library.
   MonoOnlyLogProb    <- namaste/namaste.py:1345-1349   (also accepts an ensemble [W, 6])
   MonoOnlyNegLogProb <- namaste/namaste.py:1351-1352
   CalcTdur / CalcVel <- namaste/namaste.py:1469-1477
+  calcminp / calcmaxvel / monoPriors / initLD / BuildMeanPriors
+                     <- namaste/namaste.py:947-955, :938-945, :1060-1067, :475-480 (prior construction)
+  transit_window_mask / initial_walkers / trim_samples
+                     <- namaste/namaste.py:550-556, :537-547, :597-608 (RunMCMC set-up and trimming)
 """
 from collections import OrderedDict
 
@@ -16,7 +20,8 @@ import numpy as np
 from . import core
 
 __all__ = ["MonotransitModel", "MonoLnPrior", "MonoOnlyLogProb", "MonoOnlyNegLogProb", "CalcTdur", "CalcVel",
-           "stage_lightcurve", "clear_cache"]
+           "stage_lightcurve", "clear_cache", "calcminp", "calcmaxvel", "monoPriors", "initLD", "BuildMeanPriors",
+           "transit_window_mask", "initial_walkers", "trim_samples"]
 
 _LC_CACHE = OrderedDict()
 _LC_CACHE_MAX = 8
@@ -164,3 +169,94 @@ def CalcTdur(vel, b, p):
 def CalcVel(Tdur, b, p):
     """Velocity [Rs/day] from transit duration (namaste.py:1474-1477)."""
     return (2 * (1 + p) * np.sqrt(1 - (b / (1 + p)) ** 2)) / Tdur
+
+
+# ---- prior construction feeding MonoLnPrior (once per star, host side) ----------------------------
+def calcminp(lc, tcen, tdur):
+    """Shortest period compatible with seeing a single transit (Monotransit.calcminp,
+    namaste.py:947-955): the distance from ``tcen`` to the first ``tdur``-wide jump in |t - tcen|
+    taken in array order (or to the farthest point if there is none) plus a third of the duration."""
+    dist = abs(np.asarray(lc)[:, 0] - tcen)
+    dur_jumps = np.where(np.diff(dist) > tdur)[0]
+    if len(dur_jumps) == 0:
+        return np.max(dist) + tdur * 0.33
+    return dist[dur_jumps[0]] + tdur * 0.33
+
+
+def calcmaxvel(lc, sdenss, tcen, tdur):
+    """Maximum transverse velocity [Rs/day] from the stellar-density PDF (Monotransit.calcmaxvel,
+    namaste.py:938-945).  Returns (maxvel, maxveluerr, maxvelderr, minp)."""
+    minp = calcminp(lc, tcen, tdur)
+    maxvels = ((18226 * abs(np.asarray(sdenss, dtype=np.float64))) / minp) ** (1 / 3.0)
+    prcnts = np.percentile(maxvels, [15.865525393145707, 50.0, 84.13447460685429])
+    return prcnts[1], prcnts[2] - prcnts[1], prcnts[1] - prcnts[0], minp
+
+
+def monoPriors(tcen, tdur, maxvel, maxveluerr, name="mean"):
+    """Box + density prior rows of one transit (Monotransit.monoPriors, namaste.py:1060-1067)."""
+    return OrderedDict([
+        (name + ":tcen", [tcen - tdur * 0.3, tcen + tdur * 0.3]),
+        (name + ":b", [0.0, 1.25]),
+        (name + ":vel", [0, maxvel + 5 * maxveluerr, "normlim", maxvel, maxveluerr]),
+        (name + ":RpRs", [0.02, 0.25]),
+    ])
+
+
+def initLD(LD1s, LD2s):
+    """Limb-darkening prior rows from the LD coefficient PDFs (Star.initLD, namaste.py:475-480)."""
+    return OrderedDict([
+        ("LD1", [0, 1.0, "gaussian", np.median(LD1s), np.std(LD1s)]),
+        ("LD2", [0, 1.0, "gaussian", np.median(LD2s), np.std(LD2s)]),
+    ])
+
+
+def BuildMeanPriors(lc, tcen, tdur, sdenss, LD1s, LD2s, name="mean"):
+    """The ordered six-row priors mapping MonoOnlyLogProb expects (namaste.py:1316: entry n applies
+    to params[n]), assembled the way Star.BuildMeanPriors does: the transit rows, then the LD rows
+    under the same ``name:`` prefix."""
+    maxvel, maxveluerr, _, _ = calcmaxvel(lc, sdenss, tcen, tdur)
+    priors = monoPriors(tcen, tdur, maxvel, maxveluerr, name)
+    for key, row in initLD(LD1s, LD2s).items():
+        priors[name + ":" + key] = row
+    return priors
+
+
+def transit_window_mask(t, tcen, vel, b, RpRs, ndurswindow=6, two_sided=False):
+    """Time window RunMCMC fits (namaste.py:550-556).  The reference takes ``abs()`` of a boolean,
+    which keeps everything *before* ``tcen + ndurswindow * Tdur`` (quirk Q6 of SURVEY.md);
+    ``two_sided=True`` gives the intended |t - tcen| < ndurswindow * Tdur."""
+    t = np.asarray(t, dtype=np.float64)
+    width = ndurswindow * CalcTdur(vel, b, RpRs)
+    if two_sided:
+        return np.abs(t - tcen) < width
+    return abs(t - tcen < width).astype(bool)
+
+
+def initial_walkers(pdfs, nwalkers, rng=None):
+    """Initial ensemble drawn from the parameter PDFs (namaste.py:537-547): ``nwalkers`` distinct rows
+    of the [npdf, 6] sample table (tcen, b, vel, RpRs, LD1, LD2); NaNs are replaced by
+    ``nanmedian(isnan(column))`` = 0.0 as the reference does (quirk Q5)."""
+    pdfs = np.asarray(pdfs, dtype=np.float64)
+    rng = np.random if rng is None else rng
+    chx = rng.choice(len(pdfs), nwalkers, replace=False)
+    pos = pdfs[chx].copy()
+    for col in range(pos.shape[1]):
+        bad = np.isnan(pos[:, col])
+        pos[bad, col] = np.nanmedian(bad)
+    return pos
+
+
+# ---- post-run trimming (namaste.py:597-608) --------------------------------------------------------
+def trim_samples(chain, lnprobability, nsteps):
+    """Burn-in cut and failed-walker filter of RunMCMC.  ``chain`` is [W, T, ndim], ``lnprobability``
+    [W, T].  Returns (samples [n, ndim + 1] with the log-probability as last column, good_wlkrs, ncut)."""
+    chain = np.asarray(chain)
+    lnprobability = np.asarray(lnprobability)
+    ncut = np.min([int(nsteps * 0.25), 3000])
+    prcnt = np.percentile(lnprobability[:, ncut:], [50, 95], axis=1)
+    # "failed" walkers: 95th percentile below the median of the walkers' medians
+    good_wlkrs = (prcnt[1] > np.median(prcnt[0]))
+    ndim = chain.shape[-1]
+    samples = chain[good_wlkrs, ncut:, :].reshape((-1, ndim))
+    samples = np.column_stack((samples, lnprobability[good_wlkrs, ncut:].reshape(-1)))
+    return samples, good_wlkrs, ncut

@@ -301,3 +301,24 @@ def prior_table(priors):
         else:
             rows.append([row[0], row[1], 0.0, 0.0, 0.0, 0.0])
     return np.array(rows, dtype=float)
+
+
+# ---- post-run trimming (namaste/namaste.py:597-608), written walker by walker ----------------------
+def trim_samples(chain, lnprobability, nsteps):
+    """Reference: ncut = min(int(0.25 nsteps), 3000); a walker is kept when the 95th percentile of its
+    post-burn-in lnprob exceeds the median over walkers of the per-walker medians; the kept walkers'
+    post-burn-in samples are flattened walker-major with the lnprob appended as last column."""
+    ncut = min(int(nsteps * 0.25), 3000)
+    nw = len(chain)
+    med = [float(np.percentile(lnprobability[w, ncut:], 50)) for w in range(nw)]
+    p95 = [float(np.percentile(lnprobability[w, ncut:], 95)) for w in range(nw)]
+    thresh = float(np.median(med))
+    rows = []
+    good = []
+    for w in range(nw):
+        keep = p95[w] > thresh
+        good.append(keep)
+        if keep:
+            for tt in range(ncut, chain.shape[1]):
+                rows.append(list(chain[w, tt, :]) + [lnprobability[w, tt]])
+    return np.array(rows), np.array(good), ncut

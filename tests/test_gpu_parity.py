@@ -168,3 +168,43 @@ def test_fp32_variant(nb, name, mode):
     print(name, mode, "fp32 max rel lnprob", r.max(), "ll", rl.max())
     assert r.max() < FP32_RTOL and rl.max() < FP32_RTOL
     lc.close()
+
+
+def test_degenerate_limb_darkening_matches_oracle(nb):
+    """1 - LD1/3 - LD2/6 == 0 (or non-finite LD) makes the reference's flux NaN / inf everywhere, also
+    out of transit; the sweep must not take its 'model == 1' shortcut for such walkers."""
+    from oracle import namaste_oracle as o
+    g = load_golden("synth_k2_s11")
+    lc, S = g["lc"][:600], int(g["oversamp"])
+    pos = np.repeat(g["walkers"][:1], 6, axis=0)
+    pos[:, 0] = lc[300, 0] + 0.003
+    pos[1, 4:] = [3.0, 0.0]            # four_omega == 0
+    pos[2, 4:] = [0.0, 6.0]            # four_omega == 0 through LD2
+    pos[3, 4] = np.inf
+    pos[4, 5] = -np.inf
+    pos[5, 4:] = [1.5, 3.0]            # four_omega == 0, both non-zero
+    pri = priors_from_table(g["priors"])
+    with np.errstate(all="ignore"):
+        ref = o.lnprob_ensemble(pos, lc, pri, S)
+    staged = nb.LightCurve(lc, oversamp=S)
+    for mode in ("brute", "windowed", "fused"):
+        got = staged.lnprob(pos, pri, mode=mode)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (mode, got, ref)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isinf(got), np.isinf(ref)), (mode, got, ref)
+        assert rel(got[ok], ref[ok]).max() < LNPROB_RTOL_TIGHT, mode
+    staged.close()
+
+
+def test_results_do_not_depend_on_the_launch_shape(nb):
+    """Partial sums are tied to per-light-curve granules and per-walker slots, so a walker's lnprob has
+    the same bits whatever ensemble it is evaluated in (what makes walker-split chains identical)."""
+    g = load_golden("synth_kepler_s15")
+    lc = nb.LightCurve(g["lc"], oversamp=int(g["oversamp"]))
+    pos = np.tile(g["walkers"], (12, 1))[:280]
+    for mode in ("brute", "windowed"):
+        full = lc.lnprob(pos, g["priors"], mode=mode)
+        for lo, hi in ((0, 1), (3, 40), (100, 280), (17, 147)):
+            part = lc.lnprob(pos[lo:hi], g["priors"], mode=mode)
+            assert np.array_equal(part, full[lo:hi], equal_nan=True), (mode, lo, hi)
+    lc.close()
