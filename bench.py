@@ -236,7 +236,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "wt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -433,12 +433,26 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": rate, "unit": "wt/s", "cores": cores, "kind": "port",
                                 "sample": "%d walker evaluations of the same workload (N=%d, S=%d) in %.1f s, "
                                           "NumPy oracle in a %d-process pool" % (nwalk, N, S, dt, cores)}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """Print the one JSON line on the real stdout (see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) write to fd 1; the driver expects exactly
+    # one JSON line there, so everything else is diverted to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

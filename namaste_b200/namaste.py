@@ -12,6 +12,8 @@ Namaste user can switch imports; all arithmetic runs in the CUDA library.
                      <- namaste/namaste.py:947-955, :938-945, :1060-1067, :475-480 (prior construction)
   transit_window_mask / initial_walkers / trim_samples
                      <- namaste/namaste.py:550-556, :537-547, :597-608 (RunMCMC set-up and trimming)
+  Optimize_mono      <- namaste/namaste.py:1010-1057 (multi-start L-BFGS-B; the stencils of all starts
+                        are evaluated as one ensemble per round)
 """
 from collections import OrderedDict
 
@@ -21,7 +23,7 @@ from . import core
 
 __all__ = ["MonotransitModel", "MonoLnPrior", "MonoOnlyLogProb", "MonoOnlyNegLogProb", "CalcTdur", "CalcVel",
            "stage_lightcurve", "clear_cache", "calcminp", "calcmaxvel", "monoPriors", "initLD", "BuildMeanPriors",
-           "transit_window_mask", "initial_walkers", "trim_samples"]
+           "transit_window_mask", "initial_walkers", "trim_samples", "Optimize_mono"]
 
 _LC_CACHE = OrderedDict()
 _LC_CACHE_MAX = 8
@@ -260,3 +262,102 @@ def trim_samples(chain, lnprobability, nsteps):
     samples = chain[good_wlkrs, ncut:, :].reshape((-1, ndim))
     samples = np.column_stack((samples, lnprobability[good_wlkrs, ncut:].reshape(-1)))
     return samples, good_wlkrs, ncut
+
+
+# ---- multi-start optimisation of the transit parameters (namaste.py:1010-1057) -----------------
+class _BatchedObjective(object):
+    """Lets several scipy optimisers, each running in its own thread, share one GPU call per round:
+    every optimiser posts the rows it needs (its point and the forward-difference stencil), the last
+    one to arrive evaluates all posted rows as a single ensemble and wakes the others."""
+
+    def __init__(self, evaluate, nclients):
+        import threading
+        self.evaluate = evaluate
+        self.cv = threading.Condition()
+        self.active = nclients
+        self.pending = {}
+        self.results = {}
+        self.generation = 0
+        self.ncalls = 0
+
+    def _flush(self):
+        keys = list(self.pending.keys())
+        rows = np.concatenate([self.pending[k] for k in keys], axis=0)
+        vals = self.evaluate(rows)
+        self.ncalls += 1
+        at = 0
+        for k in keys:
+            n = len(self.pending[k])
+            self.results[k] = vals[at:at + n]
+            at += n
+        self.pending.clear()
+        self.generation += 1
+        self.cv.notify_all()
+
+    def call(self, key, rows):
+        with self.cv:
+            self.pending[key] = rows
+            if len(self.pending) == self.active:
+                self._flush()
+            else:
+                gen = self.generation
+                while self.generation == gen:
+                    self.cv.wait()
+            return self.results.pop(key)
+
+    def leave(self):
+        with self.cv:
+            self.active -= 1
+            if self.active > 0 and len(self.pending) == self.active:
+                self._flush()
+
+
+def Optimize_mono(flatlc, priors, starts, tcen=None, tdur=None, monomodel=None, eps=1e-8, mode="windowed",
+                  options=None):
+    """Multi-start L-BFGS-B fit of (tcen, b, vel, RpRs, LD1, LD2) as Monotransit.Optimize_mono does
+    (namaste.py:1010-1057): the light curve is cut to |t - tcen| < 5 tdur (when both are given), every
+    row of ``starts`` seeds one ``scipy.optimize.minimize(MonoOnlyNegLogProb, x0, method="L-BFGS-B")``
+    and the successful, non-NaN results are ranked by negative log-probability.
+
+    The optimiser is scipy's own; what changes is where the objective runs: each optimiser asks for
+    its point and the six forward-difference neighbours (scipy's default gradient for L-BFGS-B, step
+    ``eps`` = 1e-8), and the requests of all starts of a round are evaluated as ONE ensemble on the GPU.
+    Returns (bestres [7] = best parameters + its negative log-probability, suc_res [n_success, 7])."""
+    import threading
+    import scipy.optimize as opt
+    flatlc = np.asarray(flatlc, dtype=np.float64)
+    if tcen is not None and tdur is not None:
+        flatlc = flatlc[abs(flatlc[:, 0] - tcen) < 5 * tdur]
+    flatlc = np.ascontiguousarray(flatlc)
+    starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
+    oversamp = getattr(monomodel, "oversamp", 10) if monomodel is not None else 10
+    staged = stage_lightcurve(flatlc, oversamp)
+    batch = _BatchedObjective(lambda rows: -1 * staged.lnprob(rows, priors, mode=mode), len(starts))
+    results = [None] * len(starts)
+
+    def run(i):
+        def fun_and_grad(x):
+            rows = np.repeat(x[None, :], 7, axis=0)
+            rows[1:] += eps * np.eye(6)
+            f = batch.call(i, rows)
+            return f[0], (f[1:] - f[0]) / eps
+        try:
+            results[i] = opt.minimize(fun_and_grad, starts[i], jac=True, method="L-BFGS-B", options=options)
+        finally:
+            batch.leave()
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(starts))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    suc = [np.hstack((r.x, r.fun)) for r in results if r is not None and r.success]
+    if len(suc) == 0:
+        raise ValueError("No successful Monotransit minimizations")
+    suc_res = np.vstack(suc)
+    suc_res = suc_res[~np.isnan(suc_res[:, -1]), :]
+    bestres = suc_res[np.argmin(suc_res[:, -1])]
+    if monomodel is not None:
+        monomodel.set_parameter_vector(bestres[:-1])
+    Optimize_mono.last_gpu_calls = batch.ncalls
+    return bestres, suc_res
