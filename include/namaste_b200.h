@@ -46,6 +46,10 @@ extern "C" {
 #define NMB_MODE_WINDOWED 1 /* exact: out-of-transit chi^2 from prefix sums, window only  */
 #define NMB_MODE_FUSED 2    /* brute force in one launch (small problems / diagnostics)     */
 
+/* GP noise-model kernels (namaste/namaste.py:279-314) */
+#define NMB_GP_REAL 0  /* celerite RealTerm(log_a, log_c) + JitterTerm(log_sigma)                    */
+#define NMB_GP_QUASI 1 /* RotationTerm(log_amp, log_timescale, log_period, log_factor) + JitterTerm  */
+
 /* arithmetic type of the transit model */
 #define NMB_F64 64
 #define NMB_F32 32
@@ -124,6 +128,18 @@ int64_t nmb_sampler_steps(const nmb_sampler* s); /* steps taken (RNG counter) */
 int nmb_sampler_get(nmb_sampler* s, int what, void* out);
 void* nmb_sampler_devptr(nmb_sampler* s, int what /*0 pos, 1 lnp*/);
 void* nmb_sampler_stream(nmb_sampler* s);
+
+/* ---- GP objective: MonoLogProb(params, lc, priors, gp) (namaste/namaste.py:1334-1339) ------------
+ * = celerite GP log-likelihood of flux - MonotransitModel(t) under the kernel + MonoLnPrior, for an
+ * ensemble.  A walker vector is celerite's GP.get_parameter_vector(): the FREE kernel parameters in
+ * kernel order (bit i of `freemask` set = parameter i of the kernel is free), then tcen, b, vel, RpRs,
+ * LD1, LD2; frozen kernel parameters are taken from `kfixed` (full kernel vector: 3 values for
+ * NMB_GP_REAL, 5 for NMB_GP_QUASI).  params [ncand][W][ndim], priors [ncand][ndim][6] (nullable),
+ * ndim = popcount(freemask) + 6.  nmb_gp_lnprob takes device pointers, nmb_gp_lnprob_host host ones. */
+int nmb_gp_lnprob(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed, int freemask,
+                  const double* priors, double* lnprob, double* loglike, void* stream);
+int nmb_gp_lnprob_host(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed, int freemask,
+                       const double* priors, double* lnprob, double* loglike);
 
 /* ---- measurement helpers (used by bench.py) ------------------------------------------------ */
 /* Sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), CUDA-event timed. */

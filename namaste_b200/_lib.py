@@ -35,6 +35,8 @@ SIGNATURES = {
     "nmb_lc_oversamp": (ctypes.c_int, [_vp]),
     "nmb_lnprob": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp]),
     "nmb_lnprob_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "nmb_gp_lnprob": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "nmb_gp_lnprob_host": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _vp]),
     "nmb_model": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, _vp]),
     "nmb_occultquad": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp,
                                       _vp]),

@@ -11,6 +11,7 @@
 
 #include "../../include/namaste_b200.h"
 #include "eval_pipeline.cuh"
+#include "gp_kernels.cuh"
 
 namespace {
 
@@ -82,7 +83,7 @@ struct nmb_lc {
     int device = 0;
     std::vector<int64_t> n;
     std::vector<double> cad;
-    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_term = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
+    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_term = nullptr, *d_var = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
     long long* d_n = nullptr;
     int *d_tgrid = nullptr, *d_gcount = nullptr;
     double *d_t0 = nullptr, *d_ginv = nullptr;
@@ -99,6 +100,9 @@ struct nmb_lc {
     size_t pin_cap = 0, stage_cap = 0;
     cudaStream_t own_stream = nullptr;
     StageTimer timer;
+    // GP objective: binned in-transit model [CW][npad] and the repacked transit parameters [CW][6]
+    double *d_modelbuf = nullptr, *d_meanpar = nullptr;
+    size_t modelbuf_cap = 0, meanpar_cap = 0;
 
     nmb::LcView view() const {
         nmb::LcView v;
@@ -115,7 +119,7 @@ extern "C" int64_t nmb_launch_count(void) { return g_launches.load(); }
 
 extern "C" void nmb_lc_destroy(nmb_lc* lc) {
     if (!lc) return;
-    cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_term); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
+    cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_term); cudaFree(lc->d_var); cudaFree(lc->d_modelbuf); cudaFree(lc->d_meanpar); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
     cudaFree(lc->d_tgrid); cudaFree(lc->d_gcount); cudaFree(lc->d_t0); cudaFree(lc->d_ginv);
     cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
     cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.wcs); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
@@ -147,7 +151,7 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
     while ((nmax + gran - 1) / gran > 512) gran *= 2;
     const int64_t padto = std::max<int64_t>(kTile, gran);
     const int64_t npad = (nmax + padto - 1) / padto * padto;
-    std::vector<double> ht(ncand * npad, 0.0), hf(ncand * npad, 1.0), hw(ncand * npad, 0.0), hterm(ncand * npad, 0.0);
+    std::vector<double> ht(ncand * npad, 0.0), hf(ncand * npad, 1.0), hw(ncand * npad, 0.0), hterm(ncand * npad, 0.0), hvar(ncand * npad, 1.0);
     std::vector<double> hph(ncand * (npad + 1), 0.0), hpl(ncand * (npad + 1), 0.0), hoff(ncand * S, 0.0);
     std::vector<double> cads(ncand);
     std::vector<double> d;
@@ -193,6 +197,7 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
             const double r = fc[i] - 1.0;
             const double term = w * (r * r);
             hterm[c * npad + i] = term;
+            hvar[c * npad + i] = ec[i] * ec[i];  // yerr**2 (celerite GP.compute)
             const double s = ph + term;
             const double bb = s - ph;
             const double e = (ph - (s - bb)) + (term - bb);
@@ -254,7 +259,7 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
     };
     cudaError_t e = cudaSuccess;
     if ((e = up(&lc->d_t, ht)) != cudaSuccess || (e = up(&lc->d_f, hf)) != cudaSuccess ||
-        (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_term, hterm)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
+        (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_term, hterm)) != cudaSuccess || (e = up(&lc->d_var, hvar)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
         (e = up(&lc->d_pre_lo, hpl)) != cudaSuccess || (e = up(&lc->d_off, hoff)) != cudaSuccess ||
         (e = up(&lc->d_t0, ht0)) != cudaSuccess || (e = up(&lc->d_ginv, hginv)) != cudaSuccess ||
         (e = cudaMalloc(&lc->d_tgrid, hgrid.size() * sizeof(int))) != cudaSuccess ||
@@ -553,6 +558,98 @@ extern "C" int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, cons
     double* d_out = lc->d_stage + np + npri;
     int rc = nmb_lnprob(lc, lc->d_stage, W, priors ? lc->d_stage + np : nullptr, d_out,
                         loglike ? d_out + C * W : nullptr, mode, dtype, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(lc->h_pin + np + npri, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::memcpy(lnprob, lc->h_pin + np + npri, C * W * sizeof(double));
+    if (loglike) std::memcpy(loglike, lc->h_pin + np + npri + C * W, C * W * sizeof(double));
+    return NMB_OK;
+}
+
+// ---- GP noise-model objective (MonoLogProb, namaste.py:1334-1339) -----------------------------------
+extern "C" int nmb_gp_lnprob(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed,
+                             int freemask, const double* priors, double* lnprob, double* loglike, void* stream) {
+    if (!lc || !params || !kfixed || !lnprob) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: null pointer");
+    if (W < 1 || W > (1 << 24)) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: W out of range");
+    if (kind != NMB_GP_REAL && kind != NMB_GP_QUASI) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: unknown kernel kind");
+    nmb::GpSpec gs{};
+    gs.kind = kind == NMB_GP_REAL ? nmb::kGpReal : nmb::kGpQuasi;
+    gs.nk = kind == NMB_GP_REAL ? 3 : 5;
+    if (freemask < 0 || freemask >= (1 << gs.nk)) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: free mask names parameters the kernel does not have");
+    gs.freemask = freemask;
+    for (int i = 0; i < gs.nk; ++i) {
+        gs.kfixed[i] = kfixed[i];
+        gs.nfree += (freemask >> i) & 1;
+    }
+    gs.ndim = gs.nfree + 6;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t CW = (size_t)lc->ncand * W;
+    if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
+    const size_t need = CW * (size_t)lc->npad;
+    if (need > lc->modelbuf_cap) {
+        if (need > ((size_t)1 << 31)) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: ensemble x light curve exceeds the 16 GiB model buffer");
+        cudaFree(lc->d_modelbuf);
+        lc->d_modelbuf = nullptr; lc->modelbuf_cap = 0;
+        CU(cudaMalloc(&lc->d_modelbuf, need * sizeof(double)));
+        lc->modelbuf_cap = need;
+    }
+    if (CW * 6 > lc->meanpar_cap) {
+        cudaFree(lc->d_meanpar);
+        lc->d_meanpar = nullptr; lc->meanpar_cap = 0;
+        CU(cudaMalloc(&lc->d_meanpar, CW * 6 * sizeof(double)));
+        lc->meanpar_cap = CW * 6;
+    }
+    nmb::gp_mean_params_kernel<<<(unsigned)((CW * 6 + 255) / 256), 256, 0, st>>>(params, (long long)CW, gs.ndim, gs.nfree,
+                                                                                lc->d_meanpar);
+    g_launches++;
+    CU(cudaGetLastError());
+    // stages 1 and 2 in model mode: ranges + binned in-transit model, nobody finishes walkers
+    lc->ws.modelbuf = lc->d_modelbuf;
+    nmb::SampleCtx sc{};
+    int rc = NMB_OK;
+    NMB_DISPATCH_S(lc->S, rc = launch_window<SS>(lc, lc->d_meanpar, (int)W, nullptr, nullptr, nullptr, st, sc, NMB_F64));
+    lc->ws.modelbuf = nullptr;
+    if (rc) return rc;
+    nmb::EvalWs ws = lc->ws;
+    ws.modelbuf = lc->d_modelbuf;
+    const unsigned blocks = (unsigned)((CW + 31) / 32);
+    if (gs.kind == nmb::kGpReal) {
+        CU(launch_pdl(nmb::gp_solve_kernel<1, 0>, dim3(blocks), dim3(32), 0, st, lc->view(), (const double*)lc->d_var, params,
+                      (int)W, gs, priors, ws, lnprob, loglike));
+    } else {
+        CU(launch_pdl(nmb::gp_solve_kernel<1, 1>, dim3(blocks), dim3(32), 0, st, lc->view(), (const double*)lc->d_var, params,
+                      (int)W, gs, priors, ws, lnprob, loglike));
+    }
+    g_launches++;
+    return NMB_OK;
+}
+
+extern "C" int nmb_gp_lnprob_host(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed,
+                                  int freemask, const double* priors, double* lnprob, double* loglike) {
+    if (!lc || !params || !kfixed || !lnprob) return fail(NMB_ERR_ARG, "nmb_gp_lnprob_host: null pointer");
+    if (W < 1) return fail(NMB_ERR_ARG, "nmb_gp_lnprob_host: W < 1");
+    const int nk = kind == NMB_GP_REAL ? 3 : 5;
+    int nfree = 0;
+    for (int i = 0; i < nk; ++i) nfree += (freemask >> i) & 1;
+    const int ndim = nfree + 6;
+    const size_t C = (size_t)lc->ncand;
+    const size_t np = C * W * ndim, npri = priors ? C * ndim * 6 : 0, nout = C * W * (loglike ? 2 : 1);
+    const size_t total = np + npri + nout;
+    if (total > lc->pin_cap) {
+        if (lc->h_pin) cudaFreeHost(lc->h_pin);
+        cudaFree(lc->d_stage);
+        lc->h_pin = nullptr; lc->d_stage = nullptr; lc->pin_cap = 0;
+        CU(cudaMallocHost(&lc->h_pin, total * sizeof(double)));
+        CU(cudaMalloc(&lc->d_stage, total * sizeof(double)));
+        lc->pin_cap = total;
+    }
+    cudaStream_t st = lc->own_stream;
+    std::memcpy(lc->h_pin, params, np * sizeof(double));
+    if (priors) std::memcpy(lc->h_pin + np, priors, npri * sizeof(double));
+    CU(cudaMemcpyAsync(lc->d_stage, lc->h_pin, (np + npri) * sizeof(double), cudaMemcpyHostToDevice, st));
+    double* d_out = lc->d_stage + np + npri;
+    int rc = nmb_gp_lnprob(lc, lc->d_stage, W, kind, kfixed, freemask, priors ? lc->d_stage + np : nullptr, d_out,
+                           loglike ? d_out + C * W : nullptr, st);
     if (rc) return rc;
     CU(cudaMemcpyAsync(lc->h_pin + np + npri, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -56,6 +56,8 @@ struct EvalWs {
                          // [3] stage-2 blocks finished; the last stage-2 block zeroes them
     int maxslots;        // slots per walker are capped; longer ranges put several passes in a slot
     int tsw;             // timestamps per pass: as many whole bins as fit in kEvalPass supersamples
+    double* modelbuf;    // GP mode only (else null): [CW][npad] binned model of the in-transit timestamps;
+                         // stage 2 stores it instead of reducing residuals and nobody finishes walkers
     unsigned long long* trace;  // diagnostics (NMB_TRACE): [16] phase envelopes in globaltimer ns, else null
 };
 
@@ -425,9 +427,11 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
         two_sum(sa, ph[ilo], sb, eb);
         eb += ea + pl[ilo];
         const double oot = sb + eb;
-        if (ihi - ilo <= 0) {  // never in transit: done here
-            const double lp = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
-            finish_walker(sc, cw, W, oot, lp, lnprob, loglike);
+        if (ihi - ilo <= 0) {  // never in transit: done here (the GP solve reads the idle range instead)
+            if (!ws.modelbuf) {
+                const double lp = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
+                finish_walker(sc, cw, W, oot, lp, lnprob, loglike);
+            }
         } else {
             ws.oot[cw] = oot;
             ws.wcs[cw] = wc;
@@ -558,7 +562,7 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
         const bool last = (s == s1);
         rec = nxt;
         if (s + 1 < s1) *reinterpret_cast<int4*>(&nxt) = __ldcg(reinterpret_cast<const int4*>(ws.slots + s + 1));
-        if (cur_cw >= 0 && (last || rec.cw != cur_cw)) {
+        if (cur_cw >= 0 && !ws.modelbuf && (last || rec.cw != cur_cw)) {
             // leaving walker cur_cw: report `seg` finished slots; the warp that completes it finishes it
             int done = 0;
             const int nsl = __ldcg(ws.nslots + cur_cw);
@@ -616,8 +620,12 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
             for (int h = lane; h < nts; h += 32) {
                 const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + h * SP)
                                          : bin_mean_rt(scratch + h * SP, Sx);
-                const double r = __ldg(gf + sub + h) - m;
-                acc += __ldg(gw_ + sub + h) * (r * r);
+                if (ws.modelbuf) {
+                    ws.modelbuf[(long long)cur_cw * lc.npad + sub + h] = m;
+                } else {
+                    const double r = __ldg(gf + sub + h) - m;
+                    acc += __ldg(gw_ + sub + h) * (r * r);
+                }
             }
             __syncwarp();
         }
