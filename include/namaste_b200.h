@@ -109,6 +109,10 @@ int nmb_lnprior(const double* params, int64_t W, int npar, const double* priors,
  * depend on the launch geometry or on how walkers are split across GPUs. */
 int nmb_sampler_create(nmb_lc* lc, int64_t W, const double* priors /*host [ncand][6][6] or NULL*/, uint64_t seed,
                        double a /*stretch scale, emcee default 2*/, int mode, nmb_sampler** out);
+/* same sampler over the GP objective MonoLogProb (see nmb_gp_lnprob for the walker layout);
+ * nwalkers must be even and >= 2 * ndim, ndim = popcount(freemask) + 6; priors [ncand][ndim][6] */
+int nmb_sampler_create_gp(nmb_lc* lc, int64_t nwalkers, int kind, const double* kfixed, int freemask,
+                          const double* priors, uint64_t seed, double a, nmb_sampler** out);
 void nmb_sampler_destroy(nmb_sampler* s);
 /* pos host [ncand][W][6]; lnp host [ncand][W] or NULL (then evaluated on the device).
  * NMB_ERR_ARG for NaN/inf parameters, NMB_ERR_NAN if an initial lnprob is NaN (emcee: ValueError). */

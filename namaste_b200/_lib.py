@@ -43,6 +43,8 @@ SIGNATURES = {
     "nmb_lnprior": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp]),
     "nmb_sampler_create": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_uint64, ctypes.c_double, ctypes.c_int,
                                           ctypes.POINTER(_vp)]),
+    "nmb_sampler_create_gp": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_uint64,
+                                             ctypes.c_double, ctypes.POINTER(_vp)]),
     "nmb_sampler_destroy": (None, [_vp]),
     "nmb_sampler_set_state": (ctypes.c_int, [_vp, _vp, _vp]),
     "nmb_sampler_run": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),

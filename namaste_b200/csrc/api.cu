@@ -567,9 +567,10 @@ extern "C" int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, cons
 }
 
 // ---- GP noise-model objective (MonoLogProb, namaste.py:1334-1339) -----------------------------------
-extern "C" int nmb_gp_lnprob(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed,
-                             int freemask, const double* priors, double* lnprob, double* loglike, void* stream) {
-    if (!lc || !params || !kfixed || !lnprob) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: null pointer");
+static int gp_lnprob_impl(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed, int freemask,
+                          const double* priors, double* lnprob, double* loglike, void* stream,
+                          const nmb::SampleCtx& gsc) {
+    if (!lc || !params || !kfixed || (!lnprob && !gsc.enabled)) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: null pointer");
     if (W < 1 || W > (1 << 24)) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: W out of range");
     if (kind != NMB_GP_REAL && kind != NMB_GP_QUASI) return fail(NMB_ERR_ARG, "nmb_gp_lnprob: unknown kernel kind");
     nmb::GpSpec gs{};
@@ -615,13 +616,19 @@ extern "C" int nmb_gp_lnprob(nmb_lc* lc, const double* params, int64_t W, int ki
     const unsigned blocks = (unsigned)((CW + 31) / 32);
     if (gs.kind == nmb::kGpReal) {
         CU(launch_pdl(nmb::gp_solve_kernel<1, 0>, dim3(blocks), dim3(32), 0, st, lc->view(), (const double*)lc->d_var, params,
-                      (int)W, gs, priors, ws, lnprob, loglike));
+                      (int)W, gs, priors, ws, lnprob, loglike, gsc));
     } else {
         CU(launch_pdl(nmb::gp_solve_kernel<1, 1>, dim3(blocks), dim3(32), 0, st, lc->view(), (const double*)lc->d_var, params,
-                      (int)W, gs, priors, ws, lnprob, loglike));
+                      (int)W, gs, priors, ws, lnprob, loglike, gsc));
     }
     g_launches++;
     return NMB_OK;
+}
+
+extern "C" int nmb_gp_lnprob(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed,
+                             int freemask, const double* priors, double* lnprob, double* loglike, void* stream) {
+    nmb::SampleCtx off{};
+    return gp_lnprob_impl(lc, params, W, kind, kfixed, freemask, priors, lnprob, loglike, stream, off);
 }
 
 extern "C" int nmb_gp_lnprob_host(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed,
@@ -759,6 +766,10 @@ struct nmb_sampler {
     nmb_lc* lc = nullptr;
     int64_t W = 0, C = 0;
     int mode = NMB_MODE_WINDOWED;
+    int ndim = 6;
+    bool gp = false;  // objective: MonoLogProb (GP noise model) instead of MonoOnlyLogProb
+    int gp_kind = 0, gp_freemask = 0;
+    double gp_kfixed[nmb::kGpMaxK] = {0, 0, 0, 0, 0};
     double a = 2.0;
     unsigned long long seed = 0;
     double *d_pos = nullptr, *d_lnp = nullptr, *d_q = nullptr, *d_zz = nullptr, *d_logu = nullptr;
@@ -786,10 +797,10 @@ int sampler_reserve(nmb_sampler* s, int64_t need) {
     int64_t cap = std::max<int64_t>(need, std::max<int64_t>(16, s->tcap * 2));
     const size_t rows = (size_t)s->C * s->W;
     double *nc = nullptr, *nl = nullptr;
-    CU(cudaMalloc(&nc, rows * cap * 6 * sizeof(double)));
+    CU(cudaMalloc(&nc, rows * cap * s->ndim * sizeof(double)));
     CU(cudaMalloc(&nl, rows * cap * sizeof(double)));
     if (s->tlen > 0) {
-        CU(cudaMemcpy2DAsync(nc, cap * 48, s->d_chain, s->tcap * 48, s->tlen * 48, rows, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaMemcpy2DAsync(nc, cap * s->ndim * 8, s->d_chain, s->tcap * s->ndim * 8, s->tlen * s->ndim * 8, rows, cudaMemcpyDeviceToDevice, s->st));
         CU(cudaMemcpy2DAsync(nl, cap * 8, s->d_lnpchain, s->tcap * 8, s->tlen * 8, rows, cudaMemcpyDeviceToDevice, s->st));
         CU(cudaStreamSynchronize(s->st));
     }
@@ -803,7 +814,7 @@ int sampler_reserve(nmb_sampler* s, int64_t need) {
 
 nmb::SampleCtx sampler_ctx(nmb_sampler* s, int half, int k0, int store) {
     nmb::SampleCtx sc{};
-    sc.enabled = 1; sc.W = (int)s->W; sc.half = half; sc.k0 = k0; sc.store = store; sc.ndim = 6;
+    sc.enabled = 1; sc.W = (int)s->W; sc.half = half; sc.k0 = k0; sc.store = store; sc.ndim = s->ndim;
     sc.step = s->step; sc.tcol = s->tlen; sc.tcap = s->tcap; sc.seed = s->seed; sc.a = s->a;
     sc.pos = s->d_pos; sc.lnp = s->d_lnp; sc.q = s->d_q; sc.zz = s->d_zz; sc.logu = s->d_logu;
     sc.chain = s->d_chain; sc.lnpchain = s->d_lnpchain; sc.nacc = s->d_nacc; sc.nan_count = s->d_nan;
@@ -831,21 +842,21 @@ extern "C" void nmb_sampler_destroy(nmb_sampler* s) {
     delete s;
 }
 
-extern "C" int nmb_sampler_create(nmb_lc* lc, int64_t W, const double* priors, uint64_t seed, double a, int mode,
-                                  nmb_sampler** out) {
+static int sampler_create_impl(nmb_lc* lc, int64_t W, int ndim, const double* priors, uint64_t seed, double a, int mode,
+                               nmb_sampler** out) {
     if (!lc || !out) return fail(NMB_ERR_ARG, "nmb_sampler_create: null pointer");
     if (W < 2 || (W % 2) != 0) return fail(NMB_ERR_ARG, "The number of walkers must be even.");
-    if (W < 2 * NMB_NPAR)
+    if (W < 2 * ndim)
         return fail(NMB_ERR_ARG, "The number of walkers needs to be more than twice the dimension of your parameter space.");
     if (!(a > 1.0)) return fail(NMB_ERR_ARG, "nmb_sampler_create: stretch scale a must be > 1");
     if (mode != NMB_MODE_BRUTE && mode != NMB_MODE_WINDOWED) return fail(NMB_ERR_ARG, "nmb_sampler_create: unknown mode");
     nmb_sampler* s = new nmb_sampler;
-    s->lc = lc; s->W = W; s->C = lc->ncand; s->mode = mode; s->a = a; s->seed = seed;
+    s->lc = lc; s->W = W; s->C = lc->ncand; s->mode = mode; s->a = a; s->seed = seed; s->ndim = ndim;
     const size_t rows = (size_t)s->C * W, hrows = (size_t)s->C * (W / 2);
     cudaError_t e = cudaSuccess;
-    if ((e = cudaMalloc(&s->d_pos, rows * 6 * sizeof(double))) != cudaSuccess ||
+    if ((e = cudaMalloc(&s->d_pos, rows * ndim * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_lnp, rows * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&s->d_q, hrows * 6 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_q, hrows * ndim * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_zz, hrows * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_logu, hrows * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_nacc, rows * sizeof(long long))) != cudaSuccess ||
@@ -857,8 +868,9 @@ extern "C" int nmb_sampler_create(nmb_lc* lc, int64_t W, const double* priors, u
         return cuda_fail(e, "nmb_sampler_create");
     }
     if (priors) {
-        if ((e = cudaMalloc(&s->d_priors, (size_t)s->C * 36 * sizeof(double))) != cudaSuccess ||
-            (e = cudaMemcpy(s->d_priors, priors, (size_t)s->C * 36 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        const size_t np = (size_t)s->C * ndim * 6;
+        if ((e = cudaMalloc(&s->d_priors, np * sizeof(double))) != cudaSuccess ||
+            (e = cudaMemcpy(s->d_priors, priors, np * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
             nmb_sampler_destroy(s);
             return cuda_fail(e, "nmb_sampler_create: priors");
         }
@@ -867,18 +879,51 @@ extern "C" int nmb_sampler_create(nmb_lc* lc, int64_t W, const double* priors, u
     return NMB_OK;
 }
 
+extern "C" int nmb_sampler_create(nmb_lc* lc, int64_t W, const double* priors, uint64_t seed, double a, int mode,
+                                  nmb_sampler** out) {
+    return sampler_create_impl(lc, W, NMB_NPAR, priors, seed, a, mode, out);
+}
+
+// Sampler over the GP objective MonoLogProb: walker vectors are [free kernel parameters, 6 transit
+// parameters] (see nmb_gp_lnprob); priors [ncand][ndim][6].
+extern "C" int nmb_sampler_create_gp(nmb_lc* lc, int64_t W, int kind, const double* kfixed, int freemask,
+                                     const double* priors, uint64_t seed, double a, nmb_sampler** out) {
+    if (!kfixed) return fail(NMB_ERR_ARG, "nmb_sampler_create_gp: null pointer");
+    if (kind != NMB_GP_REAL && kind != NMB_GP_QUASI) return fail(NMB_ERR_ARG, "nmb_sampler_create_gp: unknown kernel kind");
+    const int nk = kind == NMB_GP_REAL ? 3 : 5;
+    if (freemask < 0 || freemask >= (1 << nk)) return fail(NMB_ERR_ARG, "nmb_sampler_create_gp: bad free mask");
+    int nfree = 0;
+    for (int i = 0; i < nk; ++i) nfree += (freemask >> i) & 1;
+    if (int rc = sampler_create_impl(lc, W, nfree + 6, priors, seed, a, NMB_MODE_WINDOWED, out)) return rc;
+    nmb_sampler* s = *out;
+    s->gp = true; s->gp_kind = kind; s->gp_freemask = freemask;
+    for (int i = 0; i < nk; ++i) s->gp_kfixed[i] = kfixed[i];
+    return NMB_OK;
+}
+
+// lnprob of `W` rows (plain evaluation) or one half-step of the sampler (sc.enabled) with its objective
+static int sampler_eval(nmb_sampler* s, const double* params, int64_t W, double* lnprob, const nmb::SampleCtx& sc) {
+    if (!s->gp) return lnprob_impl(s->lc, params, W, s->d_priors, lnprob, nullptr, s->mode, NMB_F64, s->st, sc);
+    if (sc.enabled) {
+        const int n = (int)(W * s->C);
+        CU(launch_pdl(nmb::gp_propose_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64), 0, s->st, sc, (int)W, (int)s->C));
+        g_launches++;
+    }
+    return gp_lnprob_impl(s->lc, params, W, s->gp_kind, s->gp_kfixed, s->gp_freemask, s->d_priors, lnprob, nullptr, s->st, sc);
+}
+
 extern "C" int nmb_sampler_set_state(nmb_sampler* s, const double* pos, const double* lnp) {
     if (!s || !pos) return fail(NMB_ERR_ARG, "nmb_sampler_set_state: null pointer");
     const size_t rows = (size_t)s->C * s->W;
-    for (size_t i = 0; i < rows * 6; ++i)
+    for (size_t i = 0; i < rows * s->ndim; ++i)
         if (!std::isfinite(pos[i])) return fail(NMB_ERR_ARG, std::isnan(pos[i]) ? "At least one parameter value was NaN."
                                                                                 : "At least one parameter value was infinite.");
-    CU(cudaMemcpyAsync(s->d_pos, pos, rows * 6 * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_pos, pos, rows * s->ndim * sizeof(double), cudaMemcpyHostToDevice, s->st));
     if (lnp) {
         CU(cudaMemcpyAsync(s->d_lnp, lnp, rows * sizeof(double), cudaMemcpyHostToDevice, s->st));
     } else {
         nmb::SampleCtx off{};
-        if (int rc = lnprob_impl(s->lc, s->d_pos, s->W, s->d_priors, s->d_lnp, nullptr, s->mode, NMB_F64, s->st, off)) return rc;
+        if (int rc = sampler_eval(s, s->d_pos, s->W, s->d_lnp, off)) return rc;
     }
     std::vector<double> h(rows);
     CU(cudaMemcpyAsync(h.data(), s->d_lnp, rows * sizeof(double), cudaMemcpyDeviceToHost, s->st));
@@ -897,7 +942,7 @@ extern "C" int nmb_sampler_halfstep(nmb_sampler* s, int half, int64_t k0, int64_
     if (store)
         if (int rc = sampler_reserve(s, s->tlen + 1)) return rc;
     const nmb::SampleCtx sc = sampler_ctx(s, half, (int)k0, store);
-    return lnprob_impl(s->lc, s->d_q, nk, s->d_priors, nullptr, nullptr, s->mode, NMB_F64, s->st, sc);
+    return sampler_eval(s, s->d_q, nk, nullptr, sc);
 }
 
 // Close a step driven through nmb_sampler_halfstep: advance the RNG step, count a stored column.
@@ -928,8 +973,7 @@ extern "C" int nmb_sampler_run(nmb_sampler* s, int64_t nsteps, int64_t thin, int
         const int st_col = (store && (i % thin == 0)) ? 1 : 0;
         for (int half = 0; half < 2; ++half) {
             const nmb::SampleCtx sc = sampler_ctx(s, half, 0, st_col);
-            if (int rc = lnprob_impl(s->lc, s->d_q, halfk, s->d_priors, nullptr, nullptr, s->mode, NMB_F64, s->st, sc))
-                return rc;
+            if (int rc = sampler_eval(s, s->d_q, halfk, nullptr, sc)) return rc;
         }
         s->step += 1;
         if (st_col) s->tlen += 1;
@@ -958,10 +1002,10 @@ extern "C" int nmb_sampler_get(nmb_sampler* s, int what, void* out) {
     if (!s || !out) return fail(NMB_ERR_ARG, "nmb_sampler_get: null pointer");
     const size_t rows = (size_t)s->C * s->W;
     switch (what) {
-        case 0: CU(cudaMemcpyAsync(out, s->d_pos, rows * 48, cudaMemcpyDeviceToHost, s->st)); break;
+        case 0: CU(cudaMemcpyAsync(out, s->d_pos, rows * s->ndim * 8, cudaMemcpyDeviceToHost, s->st)); break;
         case 1: CU(cudaMemcpyAsync(out, s->d_lnp, rows * 8, cudaMemcpyDeviceToHost, s->st)); break;
         case 2:
-            if (s->tlen) CU(cudaMemcpy2DAsync(out, s->tlen * 48, s->d_chain, s->tcap * 48, s->tlen * 48, rows, cudaMemcpyDeviceToHost, s->st));
+            if (s->tlen) CU(cudaMemcpy2DAsync(out, s->tlen * s->ndim * 8, s->d_chain, s->tcap * s->ndim * 8, s->tlen * s->ndim * 8, rows, cudaMemcpyDeviceToHost, s->st));
             break;
         case 3:
             if (s->tlen) CU(cudaMemcpy2DAsync(out, s->tlen * 8, s->d_lnpchain, s->tcap * 8, s->tlen * 8, rows, cudaMemcpyDeviceToHost, s->st));

@@ -39,11 +39,20 @@ __global__ void gp_mean_params_kernel(const double* __restrict__ params, long lo
     mean[i] = params[w * ndim + nfree + d];
 }
 
+// stretch-move proposals of the GP sampler: one thread per evaluated walker (the transit-only sampler
+// proposes inside its stage-1 kernels instead)
+__global__ void gp_propose_kernel(SampleCtx sc, int Weval, int ncand) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Weval * ncand) return;
+    propose_stretch(sc, i / Weval, i % Weval, Weval);
+}
+
 template <int JR, int JC>
 __global__ void __launch_bounds__(32)
 gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restrict__ params, int W, GpSpec gs,
                 const double* __restrict__ priors, EvalWs ws, double* __restrict__ lnprob,
-                double* __restrict__ loglike) {
+                double* __restrict__ loglike, SampleCtx sc) {
     constexpr int J = JR + 2 * JC;
     pdl_wait();
     const long long cw = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -147,9 +156,8 @@ gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restr
         tprev = ti;
     }
     const double ll = -0.5 * ((quad + logdet) + n * 1.8378770664093453);  // log(2 pi)
-    if (loglike) loglike[cw] = ll;
     const double lp = priors ? ln_prior_dev(par, priors + (long long)cand * gs.ndim * 6, gs.ndim) : 0.0;
-    lnprob[cw] = ll + lp;
+    finish_walker(sc, cw, W, ll, lp, lnprob, loglike);
     // leave the range workspace idle for the next evaluation
     ws.rlo[cw] = INT_MAX;
     ws.rhi[cw] = 0;

@@ -59,8 +59,9 @@ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
 // Proposal for evaluated walker `k` (index within this launch) of candidate `cand`: a pure function
 // of (seed, step, half, candidate, walker) and the current positions, so several thread blocks may
 // recompute it; exactly one of them stores it (propose_store).
+constexpr int kMaxDim = 12;  // 6 transit parameters + up to 5 kernel parameters of the GP objective
 struct Proposal {
-    double q[6];
+    double q[kMaxDim];
     double zz, u_a;
 };
 __device__ __forceinline__ Proposal propose_compute(const SampleCtx& sc, int cand, int k) {
@@ -85,13 +86,15 @@ __device__ __forceinline__ Proposal propose_compute(const SampleCtx& sc, int can
     const double* s = sc.pos + ((long long)cand * sc.W + i) * sc.ndim;
     const double* c = sc.pos + ((long long)cand * sc.W + c_base + j) * sc.ndim;
 #pragma unroll
-    for (int d = 0; d < 6; ++d) pr.q[d] = c[d] - pr.zz * (c[d] - s[d]);
+    for (int d = 0; d < kMaxDim; ++d)
+        if (d < sc.ndim) pr.q[d] = c[d] - pr.zz * (c[d] - s[d]);
     return pr;
 }
 __device__ __forceinline__ void propose_store(const SampleCtx& sc, const Proposal& pr, int cand, int k, int Weval) {
     const long long e = (long long)cand * Weval + k;
 #pragma unroll
-    for (int d = 0; d < 6; ++d) sc.q[e * 6 + d] = pr.q[d];
+    for (int d = 0; d < kMaxDim; ++d)
+        if (d < sc.ndim) sc.q[e * sc.ndim + d] = pr.q[d];
     sc.zz[e] = pr.zz;
     sc.logu[e] = log(pr.u_a);
 }

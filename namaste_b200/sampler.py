@@ -5,16 +5,17 @@ Mirrors the surface Namaste uses (namaste/namaste.py:583-608; Example.ipynb cell
 (successive calls append), ``.chain [W, T, dim]``, ``.lnprobability [W, T]``, ``.flatchain``,
 ``.flatlnprobability``, ``.acceptance_fraction``, ``.naccepted``, ``.iterations``, ``.reset()``.
 
-``lnpostfn`` must be this package's ``MonoOnlyLogProb``: proposal, likelihood and accept/reject then
-run on the GPU with no per-step host round trip.  Any other callable raises ``TypeError`` (there is
-no CPU fallback).  Random numbers are Philox4x32-10 (counter based), not NumPy's Mersenne Twister:
+``lnpostfn`` must be this package's ``MonoOnlyLogProb`` (args = (lc, priors[, monomodel]),
+namaste.py:590) or ``MonoLogProb`` (GP noise model, args = (lc, priors, gp), namaste.py:583): proposal,
+likelihood and accept/reject then run on the GPU with no per-step host round trip.  Any other callable
+raises ``TypeError`` (there is no CPU fallback).  Random numbers are Philox4x32-10 (counter based), not NumPy's Mersenne Twister:
 chains agree with emcee's in distribution, not draw by draw; ``rstate0`` only seeds the stream.
 """
 import ctypes
 
 import numpy as np
 
-from . import core, namaste as _nm
+from . import core, gp as _gp, namaste as _nm
 from ._lib import MODES, check, load, ptr, as_f64
 
 __all__ = ["EnsembleSampler"]
@@ -40,11 +41,20 @@ def _seed_from(rstate0, seed):
 class EnsembleSampler(object):
     def __init__(self, nwalkers, dim, lnpostfn, a=2.0, args=(), kwargs=None, threads=1, pool=None,
                  live_dangerously=False, mode="windowed", seed=None):
-        if lnpostfn not in (_nm.MonoOnlyLogProb,):
+        if lnpostfn not in (_nm.MonoOnlyLogProb, _gp.MonoLogProb):
             raise TypeError("namaste_b200.EnsembleSampler runs the log-probability on the GPU and only accepts "
-                            "namaste_b200.MonoOnlyLogProb as lnpostfn (no CPU fallback)")
-        if dim != 6:
-            raise ValueError("MonoOnlyLogProb has 6 parameters (tcen, b, vel, RpRs, LD1, LD2); got dim=%r" % (dim,))
+                            "namaste_b200.MonoOnlyLogProb or namaste_b200.MonoLogProb as lnpostfn (no CPU fallback)")
+        self._gp = None
+        if lnpostfn is _gp.MonoLogProb:
+            if len(args) < 3 or not isinstance(args[2], _gp.GP):
+                raise ValueError("args must be (lc, priors, gp) as in namaste.py:583")
+            self._gp = args[2]
+            self._gpspec = _gp._kernel_spec(self._gp.kernel)
+            want = bin(self._gpspec[2]).count("1") + 6
+        else:
+            want = 6
+        if dim != want:
+            raise ValueError("this objective has %d parameters; got dim=%r" % (want, dim))
         if nwalkers % 2 != 0:
             raise AssertionError("The number of walkers must be even.")
         if nwalkers < 2 * dim:
@@ -55,10 +65,10 @@ class EnsembleSampler(object):
         self.k, self.dim, self.a = int(nwalkers), int(dim), float(a)
         self.args, self.threads = args, threads  # threads is accepted and ignored (one GPU does the work)
         lc, priors = args[0], args[1]
-        model = args[2] if len(args) > 2 else None
+        model = self._gp.mean if self._gp is not None else (args[2] if len(args) > 2 else None)
         self._oversamp = getattr(model, "oversamp", 10) if model is not None else 10
         self._lc = lc if isinstance(lc, core.LightCurve) else _nm.stage_lightcurve(lc, self._oversamp)
-        self._ptab = core.prior_table(priors)
+        self._ptab = core.prior_table(priors, npar=self.dim)
         self._mode, self._seed0 = mode, seed
         self._h = None
         self._have_state = False
@@ -72,10 +82,16 @@ class EnsembleSampler(object):
         lib = load()
         tab = None
         if self._ptab is not None:
-            tab = np.ascontiguousarray(np.broadcast_to(self._ptab, (self._lc.ncand, 6, 6)))
+            tab = np.ascontiguousarray(np.broadcast_to(self._ptab, (self._lc.ncand, self.dim, 6)))
         h = ctypes.c_void_p()
-        check(lib.nmb_sampler_create(self._lc._h, self.k, ptr(tab), ctypes.c_uint64(_seed_from(rstate0, self._seed0)),
-                                     self.a, MODES[self._mode], ctypes.byref(h)), "EnsembleSampler")
+        seed = ctypes.c_uint64(_seed_from(rstate0, self._seed0))
+        if self._gp is not None:
+            kind, kfull, mask = self._gpspec
+            check(lib.nmb_sampler_create_gp(self._lc._h, self.k, kind, ptr(as_f64(kfull)), mask, ptr(tab), seed, self.a,
+                                            ctypes.byref(h)), "EnsembleSampler")
+        else:
+            check(lib.nmb_sampler_create(self._lc._h, self.k, ptr(tab), seed, self.a, MODES[self._mode],
+                                         ctypes.byref(h)), "EnsembleSampler")
         self._h = h
 
     def __del__(self):
@@ -121,7 +137,7 @@ class EnsembleSampler(object):
         lib = load()
         C, W = self._lc.ncand, self.k
         T = int(lib.nmb_sampler_len(self._h)) if self._h is not None else 0
-        shape = {0: (C, W, 6), 1: (C, W), 2: (C, W, T, 6), 3: (C, W, T), 4: (C, W)}[what]
+        shape = {0: (C, W, self.dim), 1: (C, W), 2: (C, W, T, self.dim), 3: (C, W, T), 4: (C, W)}[what]
         out = np.zeros(shape, dtype=np.int64 if what == 4 else np.float64)
         if self._h is not None and out.size:
             check(lib.nmb_sampler_get(self._h, what, ptr(out)), "EnsembleSampler")

@@ -89,3 +89,32 @@ def test_other_kernels_are_refused():
     import namaste_b200 as nb
     with pytest.raises(TypeError):
         nb.GP(kernel=nb.RealTerm(-14.0, 0.0) + nb.RealTerm(-12.0, 1.0), mean=nb.MonotransitModel(0, 0, 1, 0.1, 0.3, 0.3))
+
+
+def test_gp_sampler_chain_matches_cpu_oracle():
+    """RunMCMC's default objective (namaste.py:583): EnsembleSampler over MonoLogProb, on the device,
+    against the CPU stretch move driven by the GP oracle with the same Philox stream."""
+    import namaste_b200 as nb
+    from oracle import gp_oracle as go, stretch_oracle as so
+    g = load_golden("kat_epic203311200")
+    lc = g["lc"]
+    rng = np.random.default_rng(33)
+    W, nsteps, seed = 20, 12, 424242
+    vec0 = np.concatenate([[-15.0, -1.0], g["params"][0]])
+    pos0 = vec0[None, :] * (1 + 1e-4 * rng.standard_normal((W, 8)))
+    kern = nb.RealTerm(log_a=-15.0, log_c=-1.0) + nb.JitterTerm(-9.8)
+    kern.freeze_parameter("terms[1]:log_sigma")
+    gp = nb.GP(kernel=kern, mean=nb.MonotransitModel(*g["params"][0]), fit_mean=True)
+    pri = _gp_priors([("kernel:terms[0]:log_a", [-20, 0.0]), ("kernel:terms[0]:log_c", [-3, 4.5])], g["priors"])
+    s = nb.EnsembleSampler(W, 8, nb.MonoLogProb, args=(lc, pri, gp), seed=seed)
+    pos, lnp, _ = s.run_mcmc(pos0, nsteps)
+    ref_chain, ref_ln, ref_acc = so.run(
+        lambda p: np.array([go.mono_logprob(x, lc, pri, "Real", [0, 0, -9.8], [True, True, False]) for x in p]),
+        pos0, nsteps, seed)
+    assert s.chain.shape == (W, nsteps, 8)
+    assert np.array_equal(s.chain, ref_chain)
+    assert np.allclose(s.lnprobability, ref_ln, rtol=1e-10, atol=0)
+    assert np.array_equal(s.naccepted, ref_acc)
+    assert 0.05 < s.acceptance_fraction.mean() < 0.95
+    with pytest.raises(ValueError):
+        nb.EnsembleSampler(W, 6, nb.MonoLogProb, args=(lc, pri, gp))
