@@ -145,6 +145,14 @@ int nmb_gp_lnprob(nmb_lc* lc, const double* params, int64_t W, int kind, const d
 int nmb_gp_lnprob_host(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed, int freemask,
                        const double* priors, double* lnprob, double* loglike);
 
+/* ---- detrending: k2flatten.ReduceNoise (namaste/k2flatten.py:51-84; dopolyfit :5-17) ------------------
+ * One thread block per detrending step runs the clipped weighted polynomial fit of the step's window
+ * and writes f - p(t) + 1 for the box points the step owns.  Host arrays: t (shifted to start at 0),
+ * f and e (divided by the median flux) of length n; steps [nsteps][6] = wlo, blo, bhi, whi (window =
+ * [wlo, blo) U [bhi, whi), box = [blo, bhi)) and olo, ohi (owned part of the box); out [n] in/out. */
+int nmb_flatten(const double* t, const double* f, const double* e, int64_t n, const int32_t* steps, int64_t nsteps,
+                double winsize, int deg, int niter, double sigclip, double* out);
+
 /* ---- measurement helpers (used by bench.py) ------------------------------------------------ */
 /* Sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), CUDA-event timed. */
 int nmb_measure_fp64_peak(double* tflops, double* ms);

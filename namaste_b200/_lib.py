@@ -57,6 +57,8 @@ SIGNATURES = {
     "nmb_sampler_get": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "nmb_sampler_devptr": (_vp, [_vp, ctypes.c_int]),
     "nmb_sampler_stream": (_vp, [_vp]),
+    "nmb_flatten": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_double, _vp]),
     "nmb_measure_fp64_peak": (ctypes.c_int, [_c_double_p, _c_double_p]),
     "nmb_debug_trace": (ctypes.c_int, [_vp, _vp]),
     "nmb_stage_timing": (ctypes.c_int, [_vp, ctypes.c_int]),

@@ -12,6 +12,7 @@
 #include "../../include/namaste_b200.h"
 #include "eval_pipeline.cuh"
 #include "gp_kernels.cuh"
+#include "flatten_kernels.cuh"
 
 namespace {
 
@@ -727,6 +728,70 @@ extern "C" int nmb_stage_times(nmb_lc* lc, double* stage1_ms, double* stage2_ms,
     *stage2_ms = n ? lc->timer.acc2 / n : 0.0;
     if (count) *count = n;
     lc->timer.acc1 = lc->timer.acc2 = 0; lc->timer.n = 0;
+    return NMB_OK;
+}
+
+// ---- detrending (namaste/k2flatten.py ReduceNoise) ------------------------------------------------
+// t (already shifted to start at 0), f, e (already divided by the median flux): host arrays [n];
+// steps: host array [nsteps] of {wlo, blo, bhi, whi, olo, ohi} index sextets; out: host [n], entries
+// outside every owned range are left untouched.
+extern "C" int nmb_flatten(const double* t, const double* f, const double* e, int64_t n, const int32_t* steps,
+                           int64_t nsteps, double winsize, int deg, int niter, double sigclip, double* out) {
+    if (!t || !f || !e || !steps || !out) return fail(NMB_ERR_ARG, "nmb_flatten: null pointer");
+    if (n < 1 || nsteps < 1) return fail(NMB_ERR_ARG, "nmb_flatten: empty input");
+    if (deg < 0 || deg > nmb::kFlatMaxDeg) return fail(NMB_ERR_ARG, "nmb_flatten: polynomial degree must be in 0..5");
+    if (niter < 0) return fail(NMB_ERR_ARG, "nmb_flatten: niter < 0");
+    std::vector<nmb::FlatStep> hs(nsteps);
+    int maxwin = 1;
+    for (int64_t s = 0; s < nsteps; ++s) {
+        const int32_t* r = steps + 6 * s;
+        nmb::FlatStep& st = hs[s];
+        st.wlo = r[0]; st.blo = r[1]; st.bhi = r[2]; st.whi = r[3]; st.olo = r[4]; st.ohi = r[5];
+        if (st.wlo < 0 || st.whi > n || st.blo < 0 || st.bhi > n || st.blo > st.bhi || st.olo < st.blo || st.ohi > st.bhi)
+            return fail(NMB_ERR_ARG, "nmb_flatten: step indices out of range");
+        const int n1 = std::max(0, st.blo - st.wlo), n2 = std::max(0, st.whi - st.bhi);
+        if (n1 + n2 < deg + 1) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "step %lld: the fitting window holds %d points, fewer than the %d a degree-%d polynomial needs",
+                     (long long)s, n1 + n2, deg + 1, deg);
+            return fail(NMB_ERR_PRECOND, buf);
+        }
+        maxwin = std::max(maxwin, n1 + n2);
+        // abscissa scaling: centre and half-width of the window's own time span
+        const double xa = n1 > 0 ? t[st.wlo] : t[st.bhi], xb = n2 > 0 ? t[st.whi - 1] : t[st.blo - 1];
+        st.xc = 0.5 * (xa + xb);
+        st.h = std::max(0.5 * (xb - xa), 1e-12);
+        (void)winsize;
+    }
+    const size_t smem = (size_t)maxwin * (5 * sizeof(double) + 1) + 16;
+    if (smem > 200 * 1024) return fail(NMB_ERR_ARG, "nmb_flatten: fitting window too large for shared memory");
+    double *dt = nullptr, *df = nullptr, *de = nullptr, *dout = nullptr;
+    nmb::FlatStep* dsteps = nullptr;
+    auto cleanup = [&]() { cudaFree(dt); cudaFree(df); cudaFree(de); cudaFree(dout); cudaFree(dsteps); };
+    cudaError_t err = cudaSuccess;
+    if ((err = cudaMalloc(&dt, n * sizeof(double))) != cudaSuccess || (err = cudaMalloc(&df, n * sizeof(double))) != cudaSuccess ||
+        (err = cudaMalloc(&de, n * sizeof(double))) != cudaSuccess || (err = cudaMalloc(&dout, n * sizeof(double))) != cudaSuccess ||
+        (err = cudaMalloc(&dsteps, nsteps * sizeof(nmb::FlatStep))) != cudaSuccess ||
+        (err = cudaMemcpy(dt, t, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (err = cudaMemcpy(df, f, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (err = cudaMemcpy(de, e, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (err = cudaMemcpy(dout, out, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (err = cudaMemcpy(dsteps, hs.data(), nsteps * sizeof(nmb::FlatStep), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(err, "nmb_flatten: staging");
+    }
+    if (smem > 48 * 1024 &&
+        (err = cudaFuncSetAttribute(nmb::flatten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(err, "nmb_flatten: shared memory");
+    }
+    nmb::flatten_kernel<<<(unsigned)nsteps, nmb::kFlatThreads, smem>>>(dt, df, de, dsteps, deg, niter, sigclip, maxwin, dout);
+    g_launches++;
+    if ((err = cudaGetLastError()) != cudaSuccess || (err = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(err, "nmb_flatten");
+    }
+    cleanup();
     return NMB_OK;
 }
 
