@@ -99,19 +99,22 @@ class SplitEnsembleSampler(object):
             pass
 
     def run_mcmc(self, pos0, nsteps, storechain=True):
+        """Advance the replicated ensemble `nsteps` steps.  Everything of a step -- the rank's slice of
+        each half-ensemble (two launches), the all-gather of the updated slices, the chain append --
+        is ordered on the sampler's CUDA stream; the host only waits once, at the end."""
         import torch
         lib = load()
         if pos0 is not None:
             check(lib.nmb_sampler_set_state(self._h, ptr(as_f64(pos0)), None), "run_mcmc")
         sp = self.split
-        for _ in range(int(nsteps)):
-            for half in (0, 1):
-                check(lib.nmb_sampler_halfstep(self._h, half, sp.k0, sp.nk, 0), "run_mcmc")
-                check(lib.nmb_sampler_sync(self._h), "run_mcmc")      # slice updated (sampler stream)
-                allgather_half(self.pos, self.lnp, half, sp, self.group)
-                torch.cuda.current_stream().synchronize()            # replicas consistent before the next half
-            check(lib.nmb_sampler_advance(self._h, 0, 1 if storechain else 0), "run_mcmc")
-        check(lib.nmb_sampler_sync(self._h), "run_mcmc")
+        stream = torch.cuda.ExternalStream(int(lib.nmb_sampler_stream(self._h)))
+        with torch.cuda.stream(stream):
+            for _ in range(int(nsteps)):
+                for half in (0, 1):
+                    check(lib.nmb_sampler_halfstep(self._h, half, sp.k0, sp.nk, 0), "run_mcmc")
+                    allgather_half(self.pos, self.lnp, half, sp, self.group)   # NCCL orders itself after / before this stream
+                check(lib.nmb_sampler_advance(self._h, 0, 1 if storechain else 0), "run_mcmc")
+        check(lib.nmb_sampler_sync(self._h), "run_mcmc")      # one host wait + NaN check (emcee: ValueError)
         self.iterations += int(nsteps)
         return self.pos.cpu().numpy(), self.lnp.cpu().numpy()
 
