@@ -130,6 +130,12 @@ int64_t nmb_sampler_len(const nmb_sampler* s);   /* stored chain columns */
 int64_t nmb_sampler_steps(const nmb_sampler* s); /* steps taken (RNG counter) */
 /* what: 0 pos, 1 lnp, 2 chain [ncand][W][len][6], 3 lnprobability [ncand][W][len], 4 naccepted (int64) */
 int nmb_sampler_get(nmb_sampler* s, int what, void* out);
+/* Posterior reduction without moving the chain (namaste.py:597-608 + percentile summaries :643-652):
+ * ncut = min(int(0.25 nsteps), 3000); good[w] = 95th percentile of lnprobability[w, ncut:] above the
+ * median over walkers of the per-walker medians; pct[c][i][d] = np.percentile(samples[:, d], q[i]) over
+ * chain[good, ncut:, :] with the log-probability as last column (d = ndim).  Host outputs. */
+int nmb_sampler_summary(nmb_sampler* s, int64_t nsteps, const double* q, int nq, double* pct, uint8_t* good,
+                        int64_t* ncut, int64_t* nsamples);
 void* nmb_sampler_devptr(nmb_sampler* s, int what /*0 pos, 1 lnp*/);
 void* nmb_sampler_stream(nmb_sampler* s);
 

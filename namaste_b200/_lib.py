@@ -55,6 +55,8 @@ SIGNATURES = {
     "nmb_sampler_len": (ctypes.c_int64, [_vp]),
     "nmb_sampler_steps": (ctypes.c_int64, [_vp]),
     "nmb_sampler_get": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "nmb_sampler_summary": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int, _vp, _vp, ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.POINTER(ctypes.c_int64)]),
     "nmb_sampler_devptr": (_vp, [_vp, ctypes.c_int]),
     "nmb_sampler_stream": (_vp, [_vp]),
     "nmb_flatten": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_double, ctypes.c_int,

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnamaste_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["transit_math.cuh", "lnprob_kernels.cuh", "eval_pipeline.cuh", "sampler.cuh", "gp_kernels.cuh", "flatten_kernels.cuh", os.path.join("..", "..", "include", "namaste_b200.h")]
+HEADERS = ["transit_math.cuh", "lnprob_kernels.cuh", "eval_pipeline.cuh", "sampler.cuh", "gp_kernels.cuh", "flatten_kernels.cuh", "summary_kernels.cuh", os.path.join("..", "..", "include", "namaste_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,6 +13,7 @@
 #include "eval_pipeline.cuh"
 #include "gp_kernels.cuh"
 #include "flatten_kernels.cuh"
+#include "summary_kernels.cuh"
 
 namespace {
 
@@ -1079,6 +1080,136 @@ extern "C" int nmb_sampler_get(nmb_sampler* s, int what, void* out) {
         default: return fail(NMB_ERR_ARG, "nmb_sampler_get: unknown item");
     }
     CU(cudaStreamSynchronize(s->st));
+    return NMB_OK;
+}
+
+// ---- posterior reduction on the device-resident chain (namaste.py:597-608; percentiles as :643-652) ----
+// NumPy's percentile ("linear"): virtual index (n-1) q/100, the two neighbouring order statistics,
+// a + (b-a) g for g < 1/2 and b - (b-a)(1-g) otherwise.
+static double np_lerp(double a, double b, double g) {
+    const double d = b - a;
+    return g >= 0.5 ? b - d * (1.0 - g) : a + d * g;
+}
+static void np_virtual_index(long long n, double q, long long& lo, long long& hi, double& g) {
+    const double vi = (double)(n - 1) * (q / 100.0);
+    lo = (long long)std::floor(vi);
+    hi = std::min<long long>(lo + 1, n - 1);
+    g = vi - (double)lo;
+    if (lo < 0) { lo = 0; hi = 0; g = 0.0; }
+}
+
+extern "C" int nmb_sampler_summary(nmb_sampler* s, int64_t nsteps, const double* q, int nq, double* pct, uint8_t* good,
+                                   int64_t* ncut_out, int64_t* nsamples_out) {
+    if (!s || !q || !pct || !good) return fail(NMB_ERR_ARG, "nmb_sampler_summary: null pointer");
+    if (nq < 1 || nq > 16) return fail(NMB_ERR_ARG, "nmb_sampler_summary: between 1 and 16 percentiles");
+    for (int i = 0; i < nq; ++i)
+        if (!(q[i] >= 0.0 && q[i] <= 100.0)) return fail(NMB_ERR_ARG, "Percentiles must be in the range [0, 100]");
+    const long long ncut = std::min<long long>((long long)(nsteps * 0.25), 3000);
+    const long long T = s->tlen, L = T - ncut;
+    if (L < 1) return fail(NMB_ERR_ARG, "nmb_sampler_summary: the chain is not longer than the burn-in cut");
+    if (L > 0x7fffffffLL) return fail(NMB_ERR_ARG, "nmb_sampler_summary: chain too long");
+    const size_t rows = (size_t)s->C * s->W;
+    const int ndim = s->ndim, ncol = ndim + 1;
+    cudaStream_t st = s->st;
+    // 1. per walker: 50th and 95th percentile of its post-burn-in lnprob
+    long long lo50, hi50, lo95, hi95;
+    double g50, g95;
+    np_virtual_index(L, 50.0, lo50, hi50, g50);
+    np_virtual_index(L, 95.0, lo95, hi95, g95);
+    const int hranks[4] = {(int)lo50, (int)hi50, (int)lo95, (int)hi95};
+    int* d_ranks = nullptr;
+    double* d_wsel = nullptr;
+    unsigned char* d_good = nullptr;
+    nmb::ColQuery* d_queries = nullptr;
+    unsigned int* d_hist = nullptr;
+    auto cleanup = [&]() { cudaFree(d_ranks); cudaFree(d_wsel); cudaFree(d_good); cudaFree(d_queries); cudaFree(d_hist); };
+#define CUS(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) { cleanup(); return cuda_fail(e__, #call); }          \
+    } while (0)
+    CUS(cudaMalloc(&d_ranks, sizeof hranks));
+    CUS(cudaMalloc(&d_wsel, rows * 4 * sizeof(double)));
+    CUS(cudaMalloc(&d_good, rows));
+    CUS(cudaMemcpyAsync(d_ranks, hranks, sizeof hranks, cudaMemcpyHostToDevice, st));
+    nmb::walker_select_kernel<<<(unsigned)rows, nmb::kSelThreads, 0, st>>>(s->d_lnpchain, s->tcap, ncut, (int)L, 4, d_ranks, d_wsel);
+    g_launches++;
+    std::vector<double> wsel(rows * 4);
+    CUS(cudaMemcpyAsync(wsel.data(), d_wsel, rows * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUS(cudaStreamSynchronize(st));
+    // 2. failed walkers: 95th percentile not above the median (over walkers) of the medians
+    long long nsamp_total = 0;
+    std::vector<long long> ngood(s->C, 0);
+    for (int64_t c = 0; c < s->C; ++c) {
+        std::vector<double> p50(s->W), p95(s->W);
+        for (int64_t w = 0; w < s->W; ++w) {
+            const double* r = &wsel[(c * s->W + w) * 4];
+            p50[w] = np_lerp(r[0], r[1], g50);
+            p95[w] = np_lerp(r[2], r[3], g95);
+        }
+        std::vector<double> sorted = p50;
+        std::sort(sorted.begin(), sorted.end());
+        const double med = (s->W % 2) ? sorted[s->W / 2] : (sorted[s->W / 2 - 1] + sorted[s->W / 2]) / 2.0;
+        for (int64_t w = 0; w < s->W; ++w) {
+            good[c * s->W + w] = p95[w] > med ? 1 : 0;
+            ngood[c] += good[c * s->W + w];
+        }
+        nsamp_total += ngood[c] * L;
+    }
+    if (ncut_out) *ncut_out = ncut;
+    if (nsamples_out) *nsamples_out = nsamp_total;
+    // 3. percentiles of every column over the kept samples, candidate by candidate
+    const int nqueries = ncol * nq * 2;
+    CUS(cudaMalloc(&d_queries, nqueries * sizeof(nmb::ColQuery)));
+    CUS(cudaMalloc(&d_hist, (size_t)nqueries * 256 * sizeof(unsigned int)));
+    CUS(cudaMemcpyAsync(d_good, good, rows, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)nqueries * 256 * sizeof(unsigned int);
+    if (smem > 200 * 1024) { cleanup(); return fail(NMB_ERR_ARG, "nmb_sampler_summary: too many percentiles x columns"); }
+    if (smem > 48 * 1024) CUS(cudaFuncSetAttribute(nmb::column_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t c = 0; c < s->C; ++c) {
+        const long long n = ngood[c] * L;
+        double* pc = pct + c * nq * ncol;
+        if (n < 1) {
+            for (int i = 0; i < nq * ncol; ++i) pc[i] = NAN;
+            continue;
+        }
+        std::vector<nmb::ColQuery> hq(nqueries);
+        std::vector<double> gam(nq);
+        for (int i = 0; i < nq; ++i) {
+            long long lo, hi;
+            np_virtual_index(n, q[i], lo, hi, gam[i]);
+            for (int d = 0; d < ncol; ++d) {
+                hq[(d * nq + i) * 2 + 0] = {0ull, lo, d, 0};
+                hq[(d * nq + i) * 2 + 1] = {0ull, hi, d, 0};
+            }
+        }
+        CUS(cudaMemcpyAsync(d_queries, hq.data(), nqueries * sizeof(nmb::ColQuery), cudaMemcpyHostToDevice, st));
+        CUS(cudaMemsetAsync(d_hist, 0, (size_t)nqueries * 256 * sizeof(unsigned int), st));
+        const long long total = (long long)s->W * L;
+        const unsigned blocks = (unsigned)std::min<long long>(148 * 4, (total + nmb::kSelThreads - 1) / nmb::kSelThreads);
+        for (int pass = 0; pass < 8; ++pass) {
+            nmb::column_hist_kernel<<<blocks, nmb::kSelThreads, smem, st>>>(
+                s->d_chain + (size_t)c * s->W * s->tcap * ndim, s->d_lnpchain + (size_t)c * s->W * s->tcap, d_good + c * s->W,
+                s->W, s->tcap, ncut, T, ndim, pass, d_queries, nqueries, d_hist);
+            nmb::column_pick_kernel<<<(nqueries + 63) / 64, 64, 0, st>>>(d_queries, nqueries, d_hist);
+            g_launches += 2;
+        }
+        CUS(cudaMemcpyAsync(hq.data(), d_queries, nqueries * sizeof(nmb::ColQuery), cudaMemcpyDeviceToHost, st));
+        CUS(cudaStreamSynchronize(st));
+        for (int d = 0; d < ncol; ++d)
+            for (int i = 0; i < nq; ++i) {
+                auto val = [](unsigned long long k) {
+                    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+                    double v;
+                    std::memcpy(&v, &u, sizeof v);
+                    return v;
+                };
+                pc[i * ncol + d] = np_lerp(val(hq[(d * nq + i) * 2].prefix), val(hq[(d * nq + i) * 2 + 1].prefix), gam[i]);
+            }
+    }
+    CUS(cudaGetLastError());
+#undef CUS
+    cleanup();
     return NMB_OK;
 }
 

@@ -23,7 +23,7 @@ from . import core
 
 __all__ = ["MonotransitModel", "MonoLnPrior", "MonoOnlyLogProb", "MonoOnlyNegLogProb", "CalcTdur", "CalcVel",
            "stage_lightcurve", "clear_cache", "calcminp", "calcmaxvel", "monoPriors", "initLD", "BuildMeanPriors",
-           "transit_window_mask", "initial_walkers", "trim_samples", "Optimize_mono"]
+           "transit_window_mask", "initial_walkers", "trim_samples", "Optimize_mono", "VelToOrbit", "PlanetRtoM", "MonoFinalPars"]
 
 _LC_CACHE = OrderedDict()
 _LC_CACHE_MAX = 8
@@ -361,3 +361,55 @@ def Optimize_mono(flatlc, priors, starts, tcen=None, tdur=None, monomodel=None, 
         monomodel.set_parameter_vector(bestres[:-1])
     Optimize_mono.last_gpu_calls = batch.ncalls
     return bestres, suc_res
+
+
+# ---- derived planet parameters (MonoFinalPars, namaste.py:629-652; planetlib.py:1346-1373) -------------
+def VelToOrbit(vel, Rs, Ms, dens=None, ecc=0, omega=0, timebin=86400.0):
+    """Semi-major axis [AU] and period [days] of a circular orbit from the transverse velocity in
+    stellar radii per day (planetlib.VelToOrbit, planetlib.py:1346-1355)."""
+    if dens is None:
+        dens = Ms / Rs ** 3
+    Per = 18226 * dens / (vel ** 3)
+    SMA = 13.7375 * (Ms * (Rs / vel) ** 2)
+    return SMA, Per
+
+
+def PlanetRtoM(Rad):
+    """Planet mass [Mearth] from radius [Rearth] (planetlib.PlanetRtoM, planetlib.py:1367+): rocky
+    density law below 1.5, Weiss & Marcy power law to 4, a tabulated giant branch to 16, stellar above."""
+    Rearth, Mearth = 6.137e6, 5.96e24
+    Rad = np.atleast_1d(np.asarray(Rad, dtype=np.float64))
+    M = np.zeros_like(Rad)
+    small = Rad <= 1.5
+    M[small] = ((2430 + 3390 * Rad[small]) * (1.3333 * np.pi * (Rad[small] * Rearth) ** 3)) / Mearth
+    mid = (Rad > 1.5) * (Rad <= 4.0)
+    M[mid] = 2.69 * (Rad[mid] ** 0.93)
+    giants = (Rad > 4.) * (Rad <= 16.0)
+    if giants.sum() > 0:
+        xr = np.array([3.99, 9.0, 10.5, 12.0, 13.0, 14.0, 14.5, 15.5, 16.0])
+        yr = np.array([10.0, 100.0, 300.0, 1000.0, 1100.0, 1200.0, 1350.0, 5000.0, 10000.0])
+        M[giants] = np.interp(Rad[giants], xr, yr)
+    big = Rad > 16.0
+    M[big] = 333000 * (Rad[big] / 109.1) ** 1.5
+    return M
+
+
+def MonoFinalPars(samples, srads, smasss, sdenss, rows=None, sigs=(15.865525393145707, 50.0, 84.13447460685429)):
+    """Derived planet quantities of Star.MonoFinalPars (namaste.py:629-652) for sample rows ``rows`` of
+    ``samples`` [n, >=4] (tcen, b, vel, RpRs, ...) paired with the stellar PDFs: planet radius [Rearth],
+    semi-major axis [AU], period [d], mass [Mearth], RV semi-amplitude [m/s]; returns the PDFs and
+    (median, +err, -err) of each."""
+    samples = np.asarray(samples, dtype=np.float64)
+    rows = np.arange(len(srads)) if rows is None else np.asarray(rows)
+    out = {}
+    out["Rps"] = (samples[rows, 3] * 695500000 * srads) / 6.371e6
+    out["Prob_pl"] = len(out["Rps"][out["Rps"] < (1.5 * 11.2)]) / len(out["Rps"])
+    out["smas"], out["Ps"] = VelToOrbit(samples[rows, 2], srads, smasss, sdenss)
+    out["Mps"] = PlanetRtoM(out["Rps"])
+    out["Krvs"] = ((2. * np.pi * 6.67e-11) / (out["Ps"] * 86400)) ** (1. / 3.) * (out["Mps"] * 5.96e24 / ((1.96e30 * smasss) ** (2. / 3.)))
+    for val in ["Rps", "smas", "Ps", "Mps", "Krvs"]:
+        p = np.percentile(np.array(out[val]), sigs)
+        out[val[:-1]] = p[1]
+        out[val[:-1] + "uerr"] = p[2] - p[1]
+        out[val[:-1] + "derr"] = p[1] - p[0]
+    return out

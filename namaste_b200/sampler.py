@@ -170,6 +170,27 @@ class EnsembleSampler(object):
     def acceptance_fraction(self):
         return self.naccepted / float(max(self.iterations, 1))
 
+    def summary(self, nsteps=None, percentiles=(15.865525393145707, 50.0, 84.13447460685429)):
+        """RunMCMC's trimming and percentile summaries (namaste.py:597-608, :643-652) computed on the
+        device-resident chain: returns a dict with ``ncut``, ``good_wlkrs`` [W] (failed-walker filter),
+        ``nsamples`` and ``percentiles`` [len(percentiles), ndim + 1] of the kept, post-burn-in samples
+        (last column: log-probability), i.e. ``np.percentile(samples[:, d], q)`` of
+        ``namaste_b200.trim_samples(chain, lnprobability, nsteps)`` without copying the chain."""
+        lib = load()
+        if self._h is None:
+            raise ValueError("run_mcmc has never been called")
+        nsteps = self.iterations if nsteps is None else int(nsteps)
+        q = as_f64(percentiles)
+        C, W = self._lc.ncand, self.k
+        pct = np.empty((C, len(q), self.dim + 1))
+        good = np.zeros((C, W), dtype=np.uint8)
+        ncut, nsamp = ctypes.c_int64(), ctypes.c_int64()
+        check(lib.nmb_sampler_summary(self._h, nsteps, ptr(q), len(q), ptr(pct), ptr(good), ctypes.byref(ncut),
+                                      ctypes.byref(nsamp)), "summary")
+        good = good.astype(bool)
+        return {"ncut": int(ncut.value), "nsamples": int(nsamp.value), "good_wlkrs": good[0] if C == 1 else good,
+                "percentiles": pct[0] if C == 1 else pct}
+
     def reset(self):
         """Clear chain, lnprobability and acceptance counters (emcee: clear_chain/reset)."""
         if self._h is not None:
