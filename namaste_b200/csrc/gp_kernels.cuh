@@ -94,14 +94,18 @@ gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restr
     }
     (void)bq;
 
-    double S[J][J], Wv[J], fv[J], U[J], V[J], phi[J];
+    double S[J][J], Wv[J], fv[J], U[J], V[J];
 #pragma unroll
     for (int i = 0; i < J; ++i) {
         fv[i] = 0.0;
 #pragma unroll
         for (int k = 0; k < J; ++k) S[i][k] = 0.0;
     }
-    double D = 0.0, z = 0.0, quad = 0.0, logdet = 0.0, tprev = 0.0;
+    // log det K = sum log D_n is accumulated as a product of mantissas plus a sum of binary exponents
+    // (one log at the end instead of one per step); 1/D_n is formed once per step and shared by W_n and
+    // the quadratic form.  Both differ from the textbook evaluation by rounding only.
+    double D = 0.0, rD = 0.0, z = 0.0, quad = 0.0, tprev = 0.0, mant = 1.0;
+    long long esum = 0;
     for (int i = 0; i < n; ++i) {
         const double ti = __ldg(gt + i);
         const double mean = (i >= lo && i < hi) ? gm[i] : 1.0;
@@ -119,18 +123,19 @@ gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restr
         }
         if (i == 0) {
             D = A;
+            rD = 1.0 / D;
 #pragma unroll
-            for (int k = 0; k < J; ++k) Wv[k] = V[k] / D;
+            for (int k = 0; k < J; ++k) Wv[k] = V[k] * rD;
             z = r;
         } else {
             const double dt = ti - tprev;
-#pragma unroll
-            for (int k = 0; k < J; ++k) phi[k] = exp(-c[k] * dt);
+            // the rotation term's real and complex parts share one damping rate, so phi is one number
+            const double ph = exp(-c[0] * dt);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
 #pragma unroll
-                for (int k = 0; k < J; ++k) S[j][k] = (phi[j] * phi[k]) * (S[j][k] + D * (Wv[j] * Wv[k]));
-                fv[j] = phi[j] * (fv[j] + Wv[j] * z);
+                for (int k = 0; k < J; ++k) S[j][k] = (ph * ph) * (S[j][k] + D * (Wv[j] * Wv[k]));
+                fv[j] = ph * (fv[j] + Wv[j] * z);
             }
             double usu = 0.0, us[J];
 #pragma unroll
@@ -143,18 +148,26 @@ gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restr
 #pragma unroll
             for (int k = 0; k < J; ++k) usu += us[k] * U[k];
             D = A - usu;
+            rD = 1.0 / D;
             double uf = 0.0;
 #pragma unroll
             for (int k = 0; k < J; ++k) {
-                Wv[k] = (V[k] - us[k]) / D;
+                Wv[k] = (V[k] - us[k]) * rD;
                 uf += U[k] * fv[k];
             }
             z = r - uf;
         }
-        quad += z * z / D;
-        logdet += log(D);
+        quad += (z * z) * rD;
+        int e2;
+        mant *= frexp(D, &e2);
+        esum += e2;
+        if ((i & 255) == 255) {  // keep the running mantissa product away from underflow
+            mant = frexp(mant, &e2);
+            esum += e2;
+        }
         tprev = ti;
     }
+    const double logdet = log(mant) + (double)esum * 0.6931471805599453;
     const double ll = -0.5 * ((quad + logdet) + n * 1.8378770664093453);  // log(2 pi)
     const double lp = priors ? ln_prior_dev(par, priors + (long long)cand * gs.ndim * 6, gs.ndim) : 0.0;
     finish_walker(sc, cw, W, ll, lp, lnprob, loglike);
