@@ -1,0 +1,112 @@
+"""Edge cases and full-size properties of the likelihood path on the GPU: ragged candidate batches
+(BASELINE config 4), generic supersampling factors, tiny inputs, and -- at the full sizes of BASELINE
+configs 2 and 3 -- properties that do not need the oracle on every walker (brute force vs prefix-sum
+mode, invariance under permutation of the ensemble) plus oracle spot checks."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, priors_from_table
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import namaste_b200
+    return namaste_b200
+
+
+def test_ragged_candidate_batch(nb):
+    from oracle import namaste_oracle as o
+    g = load_golden("synth_tess_s10")
+    base, pos, tab = g["lc"], g["walkers"][:12], g["priors"]
+    mid = len(base) // 2
+    cuts = [(mid - 700, mid + 650), (mid - 40, mid + 23), (0, len(base)), (mid - 3000, mid + 100), (mid - 1, mid + 1)]
+    curves = [np.ascontiguousarray(base[a:b]) for a, b in cuts]
+    batch = nb.LightCurve(curves, oversamp=10)
+    assert batch.ncand == 5 and list(batch.npoints) == [b - a for a, b in cuts]
+    params = np.stack([pos + 1e-6 * k for k in range(5)])            # [5, 12, 6]
+    tabs = np.stack([tab] * 5)
+    for mode in ("brute", "windowed"):
+        got = batch.lnprob(params, tabs, mode=mode)
+        assert got.shape == (5, 12)
+        for k, lc in enumerate(curves):
+            single = nb.LightCurve(lc, oversamp=10)
+            one = single.lnprob(params[k], tab, mode=mode)
+            assert np.array_equal(got[k], one, equal_nan=True), (mode, k)   # same bits as on its own
+            single.close()
+        with np.errstate(all="ignore"):
+            ref = o.lnprob_ensemble(params[1], curves[1], priors_from_table(tab))
+        ok = np.isfinite(ref)
+        assert rel(got[1][ok], ref[ok]).max() < 1e-11, mode
+    batch.close()
+
+
+@pytest.mark.parametrize("S", [1, 3, 7, 16])
+def test_generic_supersampling_factors(nb, S):
+    """Only S = 1, 10, 11, 15 have compiled-in loops; everything else takes the run-time path."""
+    from oracle import namaste_oracle as o
+    g = load_golden("synth_k2_s11")
+    lc, pos, pri = g["lc"][1700:2300], g["walkers"][:10], priors_from_table(g["priors"])
+    with np.errstate(all="ignore"):
+        ref = o.lnprob_ensemble(pos, lc, pri, S)
+    staged = nb.LightCurve(lc, oversamp=S)
+    for mode in ("brute", "windowed", "fused"):
+        got = staged.lnprob(pos, pri, mode=mode)
+        ok = np.isfinite(ref)
+        assert rel(got[ok], ref[ok]).max() < 1e-11, (S, mode)
+    staged.close()
+
+
+@pytest.mark.parametrize("n", [2, 3, 63, 64, 65, 129])
+def test_tiny_light_curves_and_single_walker(nb, n):
+    from oracle import namaste_oracle as o
+    g = load_golden("kat_epic203311200")
+    lc, pri = g["lc"][100:100 + n], priors_from_table(g["priors"])
+    th = g["params"][0].copy()
+    th[0] = lc[n // 2, 0]
+    staged = nb.LightCurve(lc)
+    for mode in ("brute", "windowed", "fused"):
+        got = staged.lnprob(th[None, :], pri, mode=mode)
+        ref = o.mono_only_logprob(th, lc, pri)
+        assert got.shape == (1,) and abs(got[0] - ref) <= 1e-11 * abs(ref), (n, mode)
+    staged.close()
+
+
+def _workload(name):
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.make_workload(name)
+
+
+@pytest.mark.parametrize("name,nspot", [("k2", 6), ("kepler", 2)])
+def test_full_size_properties(nb, name, nspot):
+    """BASELINE configs 2 (N=4000, S=11, W=1024) and 3 (N=65000, S=15, W=4096) at full size."""
+    from oracle import namaste_oracle as o
+    wl = _workload(name)
+    staged = nb.LightCurve(wl["lc"], oversamp=wl["S"])
+    pos, tab = wl["pos"], wl["priors"]
+    brute = staged.lnprob(pos, tab, mode="brute")
+    win = staged.lnprob(pos, tab, mode="windowed")
+    assert brute.shape == (wl["W"],) and np.isfinite(brute).all()
+    # every fine sample classified vs prefix sums + window: same likelihood
+    assert rel(brute, win).max() < 1e-12
+    # the ensemble is a set: permuting the walkers permutes the results, bit for bit
+    perm = np.random.default_rng(1).permutation(wl["W"])
+    assert np.array_equal(staged.lnprob(pos[perm], tab, mode="brute"), brute[perm])
+    assert np.array_equal(staged.lnprob(pos[perm], tab, mode="windowed"), win[perm])
+    # idempotence: evaluating again gives the same bits (workspace left clean)
+    assert np.array_equal(staged.lnprob(pos, tab, mode="brute"), brute)
+    # oracle spot checks: the first walkers (uniform in the prior box) and one from the tight ball
+    pri = priors_from_table(tab)
+    for i in list(range(nspot)) + [wl["W"] - 1]:
+        ref = o.mono_only_logprob(pos[i], wl["lc"], pri, wl["S"])
+        assert abs(brute[i] - ref) <= 1e-10 * abs(ref) and abs(win[i] - ref) <= 1e-10 * abs(ref), i
+    staged.close()
