@@ -327,6 +327,10 @@ int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
         // timestamps per pass: as many whole bins as fit in kEvalPass supersamples; slots per walker:
         // one pass each up to a pool of 4 M slots over the ensemble (>= 64 per walker)
         ws.tsw = std::max(1, nmb::kEvalPass / lc->S);
+        // slots a warp evaluates in one pass: ~270 supersamples, two slots when the bins are long
+        // (measured: S = 15 prefers 2, S = 10 / 11 prefer 3-4; differences of a few per cent)
+        ws.merge = lc->S >= 13 ? 2 : 3;
+        if (const char* m = std::getenv("NMB_EVAL_MERGE")) ws.merge = std::max(1, std::min(nmb::kEvalMerge, std::atoi(m)));
         const size_t full = (size_t)(lc->npad + ws.tsw - 1) / ws.tsw;
         ws.maxslots = (int)std::min<size_t>(full, std::max<size_t>(64, (size_t)4194304 / CW));
         const size_t cap = CW * ws.maxslots;

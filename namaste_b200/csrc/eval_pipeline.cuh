@@ -55,7 +55,8 @@ struct EvalWs {
     int* counters;       // [1] slots pushed by stage 1 (queue tail), [2] next dynamically assigned chunk,
                          // [3] stage-2 blocks finished; the last stage-2 block zeroes them
     int maxslots;        // slots per walker are capped; longer ranges put several passes in a slot
-    int tsw;             // timestamps per pass: as many whole bins as fit in kEvalPass supersamples
+    int tsw;             // timestamps per slot: as many whole bins as fit in kEvalPass supersamples
+    int merge;           // consecutive slots of a walker a warp evaluates in one pass (<= kEvalMerge)
     double* modelbuf;    // GP mode only (else null): [CW][npad] binned model of the in-transit timestamps;
                          // stage 2 stores it instead of reducing residuals and nobody finishes walkers
     unsigned long long* trace;  // diagnostics (NMB_TRACE): [16] phase envelopes in globaltimer ns, else null
@@ -456,7 +457,11 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
 #ifndef NMB_EVALPASS
 #define NMB_EVALPASS 96
 #endif
-constexpr int kEvalPass = NMB_EVALPASS;  // supersamples a warp evaluates per pass
+constexpr int kEvalPass = NMB_EVALPASS;  // supersamples of one slot (the unit of the stored partial sums)
+#ifndef NMB_EVALMERGE
+#define NMB_EVALMERGE 4
+#endif
+constexpr int kEvalMerge = NMB_EVALMERGE;  // most consecutive slots of a walker a warp evaluates in one pass
 
 // PATH: 0 = general IEEE FP64, 1 = FP64 hot path (default), 2 = FP32 hot path (NMB_F32)
 template <int PATH>
@@ -509,7 +514,8 @@ __device__ __forceinline__ double sample_flux_eval<2>(double ti, double offk, co
 template <int THREADS>
 struct EvalSmem {
     // per warp: TSW bins of S fluxes at an odd stride; TSW * S <= kEvalPass
-    double scratch[THREADS / 32][2 * kEvalPass + 8];
+    // ... for up to kEvalMerge slots sharing one pass, followed by the chi^2 terms of that pass
+    double scratch[THREADS / 32][kEvalMerge * (2 * kEvalPass + 8) + kEvalMerge * kEvalPass];
     // the current walker's constants, one copy per warp: operands come from shared memory when
     // needed instead of pinning ~40 registers for the whole pass
     WalkerConsts wc[THREADS / 32];
@@ -537,8 +543,11 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
     const int nwarps = gridDim.x * NWARP;
     const int gw = (((int)blockIdx.x / nsm) * NWARP + warp) * nsm + (int)blockIdx.x % nsm;
     // chunks of slots: the first chunk of a warp is its own index (no atomic on the way to the first
-    // sample), further chunks come from a shared counter, fetched one chunk ahead
-    const int chunk = max(1, total / (nwarps * 4));
+    // sample), further chunks come from a shared counter, fetched one chunk ahead.  Small queues are
+    // dealt out in one chunk per warp; large ones in chunks of at least one merged pass.
+    const int merge = ws.merge;
+    const int per = (total + nwarps - 1) / nwarps;
+    const int chunk = per <= merge ? max(1, per) : max(merge, total / (nwarps * 8));
     const int nchunks = (total + chunk - 1) / chunk;
     int* queue = ws.counters + 2;
     int ch_cur = gw, ch_nxt = INT_MAX;
@@ -551,47 +560,56 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
     WalkerConsts& wc = sm.wc[warp];
     QuadConstsF cf = QuadConstsF{};
     const double *gt = nullptr, *gf = nullptr, *gw_ = nullptr, *goff = nullptr;
-    SlotRec rec{}, nxt{};
+    double* terms = scratch + kEvalMerge * (2 * kEvalPass + 8);  // chi^2 terms of a merged pass
+
+    // leaving a walker: report `seg` finished slots; the warp that completes it folds the slot partials
+    // in slot order, evaluates the priors and finishes the walker
+    auto leave_walker = [&]() {
+        if (cur_cw < 0 || ws.modelbuf) return;
+        int done = 0;
+        const int nsl = __ldcg(ws.nslots + cur_cw);
+        if (lane == 0 && seg < nsl) {
+            __threadfence();
+            done = atomicAdd(ws.slotsdone + cur_cw, seg);
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done + seg == nsl) {
+            if (seg < nsl) __threadfence();
+            __syncwarp();
+            const double* part = ws.slotpart + cur_first;
+            double ssum = 0.0;
+            for (int c = lane; c < nsl; c += 32) ssum += __ldcg(part + c);
+            ssum = warp_sum(ssum);
+            const double* par = (sc.enabled ? sc.q : params) + (long long)cur_cw * 6;
+            const double lp = priors ? ln_prior_warp(par, priors + (long long)(cur_cw / W) * 36, 6, lane) : 0.0;
+            if (lane == 0) {
+                finish_walker(sc, cur_cw, W, ws.oot[cur_cw] + ssum, lp, lnprob, loglike);
+                ws.slotsdone[cur_cw] = 0;
+                ws.rlo[cur_cw] = INT_MAX;
+                ws.rhi[cur_cw] = 0;
+            }
+        }
+    };
+
     if (lane == 0) trace_max(ws, 9);
     while (ch_cur < nchunks) {
       const int s0 = ch_cur * chunk, s1 = min(total, s0 + chunk);
       int ch_nn = INT_MAX;
       if (lane == 0 && ch_nxt < nchunks) ch_nn = nwarps + atomicAdd(queue, 1);
-      *reinterpret_cast<int4*>(&nxt) = __ldcg(reinterpret_cast<const int4*>(ws.slots + s0));
-      for (int s = s0; s <= s1; ++s) {
-        const bool last = (s == s1);
-        rec = nxt;
-        if (s + 1 < s1) *reinterpret_cast<int4*>(&nxt) = __ldcg(reinterpret_cast<const int4*>(ws.slots + s + 1));
-        if (cur_cw >= 0 && !ws.modelbuf && (last || rec.cw != cur_cw)) {
-            // leaving walker cur_cw: report `seg` finished slots; the warp that completes it finishes it
-            int done = 0;
-            const int nsl = __ldcg(ws.nslots + cur_cw);
-            if (lane == 0 && seg < nsl) {
-                __threadfence();
-                done = atomicAdd(ws.slotsdone + cur_cw, seg);
-            }
-            done = __shfl_sync(0xffffffffu, done, 0);
-            if (done + seg == nsl) {
-                if (seg < nsl) __threadfence();
-                __syncwarp();
-                const double* part = ws.slotpart + cur_first;
-                double ssum = 0.0;
-                for (int c = lane; c < nsl; c += 32) ssum += __ldcg(part + c);
-                ssum = warp_sum(ssum);
-                const double* par = (sc.enabled ? sc.q : params) + (long long)cur_cw * 6;
-                const double lp = priors ? ln_prior_warp(par, priors + (long long)(cur_cw / W) * 36, 6, lane) : 0.0;
-                if (lane == 0) {
-                    finish_walker(sc, cur_cw, W, ws.oot[cur_cw] + ssum, lp, lnprob, loglike);
-                    ws.slotsdone[cur_cw] = 0;
-                    ws.rlo[cur_cw] = INT_MAX;
-                    ws.rhi[cur_cw] = 0;
-                }
-            }
-        }
-        if (last) break;
-        if (rec.cw != cur_cw) {
-            cur_cw = rec.cw;
-            cur_first = rec.first;
+      int s = s0;
+      while (s < s1) {
+        // the next kEvalMerge slot records, one per lane
+        SlotRec mine;
+        mine.cw = -2; mine.t0 = 0; mine.t1 = 0; mine.first = 0;
+        if (lane < kEvalMerge && s + lane < s1)
+            *reinterpret_cast<int4*>(&mine) = __ldcg(reinterpret_cast<const int4*>(ws.slots + s + lane));
+        const int cw0 = __shfl_sync(0xffffffffu, mine.cw, 0);
+        const int t0 = __shfl_sync(0xffffffffu, mine.t0, 0);
+        int tend = __shfl_sync(0xffffffffu, mine.t1, 0);
+        if (cw0 != cur_cw) {
+            leave_walker();
+            cur_cw = cw0;
+            cur_first = __shfl_sync(0xffffffffu, mine.first, 0);
             seg = 0;
             cand = cur_cw / W;
             {
@@ -608,32 +626,80 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
             gw_ = lc.w + (long long)cand * lc.npad;
             goff = lc.off + (long long)cand * Sx;
         }
-        double acc = 0.0;
-        for (int sub = rec.t0; sub < rec.t1; sub += TSW) {
-            const int nts = min(TSW, rec.t1 - sub);
+        // how many consecutive single-pass slots of this walker can share one pass
+        int run = 1;
+        const bool single = (tend - t0 <= TSW);
+        if (single) {
+#pragma unroll
+            for (int l = 1; l < kEvalMerge; ++l) {
+                const int cwl = __shfl_sync(0xffffffffu, mine.cw, l);
+                const int t0l = __shfl_sync(0xffffffffu, mine.t0, l), t1l = __shfl_sync(0xffffffffu, mine.t1, l);
+                if (run == l && l < merge && cwl == cur_cw && t0l == tend && t1l - t0l <= TSW) { run = l + 1; tend = t1l; }
+            }
+        }
+        if (single) {
+            // ---- one pass over up to kEvalMerge slots: every lane stays busy through the flux rounds,
+            // bins and residuals are formed once, then each slot's terms are summed in its own canonical
+            // lane order so the partials do not depend on how slots were merged
+            const int nts = tend - t0;
             const int nsamp = nts * Sx;
             for (int j = lane; j < nsamp; j += 32) {
                 const int h = j / Sx, k = j - h * Sx;
-                scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + sub + h), __ldg(goff + k), wc, cf, &ws.wcs[cur_cw].q);
+                scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + t0 + h), __ldg(goff + k), wc, cf, &ws.wcs[cur_cw].q);
             }
             __syncwarp();
             for (int h = lane; h < nts; h += 32) {
                 const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + h * SP)
                                          : bin_mean_rt(scratch + h * SP, Sx);
                 if (ws.modelbuf) {
-                    ws.modelbuf[(long long)cur_cw * lc.npad + sub + h] = m;
+                    ws.modelbuf[(long long)cur_cw * lc.npad + t0 + h] = m;
                 } else {
-                    const double r = __ldg(gf + sub + h) - m;
-                    acc += __ldg(gw_ + sub + h) * (r * r);
+                    const double r = __ldg(gf + t0 + h) - m;
+                    terms[h] = __ldg(gw_ + t0 + h) * (r * r);
                 }
             }
             __syncwarp();
+            if (!ws.modelbuf) {
+                for (int q = 0; q < run; ++q) {
+                    const int b0 = q * TSW, nq = min(TSW, nts - b0);
+                    double acc = 0.0;
+                    for (int h = lane; h < nq; h += 32) acc += terms[b0 + h];
+                    acc = warp_sum(acc);
+                    if (lane == 0) ws.slotpart[s + q] = acc;
+                }
+            }
+            __syncwarp();
+        } else {
+            // ---- a slot of several passes (walkers whose range exceeds the per-walker slot cap)
+            double acc = 0.0;
+            for (int sub = t0; sub < tend; sub += TSW) {
+                const int nts = min(TSW, tend - sub);
+                const int nsamp = nts * Sx;
+                for (int j = lane; j < nsamp; j += 32) {
+                    const int h = j / Sx, k = j - h * Sx;
+                    scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + sub + h), __ldg(goff + k), wc, cf, &ws.wcs[cur_cw].q);
+                }
+                __syncwarp();
+                for (int h = lane; h < nts; h += 32) {
+                    const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + h * SP)
+                                             : bin_mean_rt(scratch + h * SP, Sx);
+                    if (ws.modelbuf) {
+                        ws.modelbuf[(long long)cur_cw * lc.npad + sub + h] = m;
+                    } else {
+                        const double r = __ldg(gf + sub + h) - m;
+                        acc += __ldg(gw_ + sub + h) * (r * r);
+                    }
+                }
+                __syncwarp();
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) ws.slotpart[s] = acc;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) ws.slotpart[s] = acc;
-        ++seg;
-        if (lane == 0) trace_max(ws, 10);  // slot evaluated
+        seg += run;
+        s += run;
+        if (lane == 0) trace_max(ws, 10);  // slots evaluated
       }
+      leave_walker();
       cur_cw = -1;
       ch_cur = ch_nxt;
       ch_nxt = __shfl_sync(0xffffffffu, ch_nn, 0);
