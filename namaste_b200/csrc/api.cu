@@ -439,8 +439,11 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     static const int force_thr = std::getenv("NMB_SWEEP_THREADS") ? std::atoi(std::getenv("NMB_SWEEP_THREADS")) : 0;
     const long long blocks128 = (long long)lc->ncand * ((W + 127) / 128) * lc->ngran;
     const bool wide = force_thr ? (force_thr == 128) : (W >= 128 || blocks128 >= 4 * 148);
-    int rc = wide ? launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc)
-                  : launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc);
+    static const int minb = std::getenv("NMB_SWEEP_MINB") ? std::atoi(std::getenv("NMB_SWEEP_MINB")) : 8;
+    int rc = !wide       ? launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc)
+             : minb == 6 ? launch_sweep_t<S, 128, 6>(lc, params, W, priors, lnprob, loglike, st, sc)
+             : minb == 4 ? launch_sweep_t<S, 128, 4>(lc, params, W, priors, lnprob, loglike, st, sc)
+                         : launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (rc) return rc;
     lc->timer.mark(1, st);
     rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);

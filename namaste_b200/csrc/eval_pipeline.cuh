@@ -149,11 +149,13 @@ __device__ __forceinline__ void push_slots(const EvalWs& ws, long long cw, int l
 // A block owns WPB*32 walkers (one per thread, constants in registers) and a span of `gpb`
 // reduction granules of one light curve.  The span streams through shared memory in chunks of CH
 // timestamps: two TMA bulk copies per chunk (t and the precomputed chi^2 terms w*(f-1)^2) into a
-// double buffer, from which the block builds the table of fine times ft[i][k] = t_i + off_k once
-// for all its walkers.  The inner loop then costs, per walker and fine sample, two DFMA
-//   vx' = fma(vel, ft, -vel*tcen),  q' = fma(vx', vx', b^2)
-// and a third of an integer 3-input min on the high words (VIMNMX3); ft arrives by broadcast
-// LDS.128, so the FP64 pipe is the only saturated unit.  A timestamp whose S samples all have
+// double buffer.  The inner loop costs, per walker and fine sample, two DFMA
+//   vx' = fma(vel, t_i, ck),  ck = fma(vel, off_k, -vel*tcen)  (S registers per walker),
+//   q'  = fma(vx', vx', b^2)
+// and a third of an integer 3-input min on the high words (VIMNMX3); t_i is one broadcast LDS per
+// timestamp.  A DFMA holds the issue port for two cycles on this part and every other instruction
+// for one, so the loop is written to keep non-FP64 instructions per sample to a minimum.  (The
+// run-time-S instantiation reads a table ft[i][k] = t_i + off_k built per chunk instead.)  A timestamp whose S samples all have
 // hi32(q') > hi32(q_thr) is provably outside the limb (see make_walker_consts) and adds its
 // precomputed term; the others only widen the walker's in-transit range, kept in registers and
 // merged with one atomicMin/Max per thread.  Per-(granule, walker) partial sums go to HBM
@@ -163,7 +165,7 @@ template <int S, int CH>
 struct WalkSmem {
     static constexpr int SR = S > 0 ? S : kMaxS;
     static constexpr int SP = (SR + 1) & ~1;  // even row stride: 16-byte aligned rows for LDS.128
-    double ftab[2][CH * SP];
+    double ftab[2][S > 0 ? 2 : CH * SP];  // fine-time table: run-time-S instantiation only
     double traw[2][CH];
     double term[2][CH];
     double off[kMaxS];
@@ -230,6 +232,13 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
     }
     __syncthreads();  // mbarrier init and offsets visible
     if (tid == 0) trace_max(ws, 1);  // constants ready
+    // compiled-in S: the walker's S sample offsets live in registers, ck = vel * off_k - vel * tcen, so a
+    // fine sample is vx' = fma(vel, t_i, ck) with t_i one broadcast load per timestamp and no table
+    double ck[S > 0 ? S : 1];
+    if (S > 0) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) ck[k] = fma(vel, sm.off[k], nvtc);
+    }
 
     double acc = 0.0;
     int lo = INT_MAX, hi = 0;
@@ -237,46 +246,39 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
     for (int c = c_begin; c < c_end; ++c) {
         const int it = c - c_begin, buf = it & 1;
         mbar_wait(&sm.mbar[buf], (it >> 1) & 1);
-        {   // fine-time table of this chunk
+        if (S == 0) {  // run-time S: fine-time table of this chunk, ft[i][k] = t_i + off_k
             const double* tr = sm.traw[buf];
             double* ft = sm.ftab[buf];
-            if (S > 0) {
-                for (int e = tid; e < CH * S; e += THREADS) {
-                    const int i = e / S, k = e - i * S;
-                    ft[i * SP + k] = tr[i] + sm.off[k];
-                }
-            } else {
-                for (int e = tid; e < CH * Sx; e += THREADS) {
-                    const int i = e / Sx, k = e - i * Sx;
-                    ft[i * SP + k] = tr[i] + sm.off[k];
-                }
+            for (int e = tid; e < CH * Sx; e += THREADS) {
+                const int i = e / Sx, k = e - i * Sx;
+                ft[i * SP + k] = tr[i] + sm.off[k];
             }
         }
-        __syncthreads();  // table complete; every thread is past the previous chunk
+        __syncthreads();  // every thread is past the previous chunk (and the table is complete)
         if (tid == 0 && c + 1 < c_end) {
             mbar_expect_tx(&sm.mbar[buf ^ 1], 2u * CH * sizeof(double));
             tma_bulk_g2s(sm.traw[buf ^ 1], gt + (long long)(c + 1) * CH, CH * sizeof(double), &sm.mbar[buf ^ 1]);
             tma_bulk_g2s(sm.term[buf ^ 1], gterm + (long long)(c + 1) * CH, CH * sizeof(double), &sm.mbar[buf ^ 1]);
         }
-        const double* ft = sm.ftab[buf];
+        const double* tr = sm.traw[buf];
         const double* tm = sm.term[buf];
         const int base = c * CH;
 #pragma unroll 2
         for (int i = 0; i < CH; ++i) {
-            const double* row = ft + i * SP;
             int qmin = INT_MAX;
             if (S > 0) {
+                const double ti = tr[i];
 #pragma unroll
                 for (int k = 0; k + 1 < S; k += 2) {
-                    const double2 f2 = *reinterpret_cast<const double2*>(row + k);
-                    const double vx0 = fma(vel, f2.x, nvtc), vx1 = fma(vel, f2.y, nvtc);
+                    const double vx0 = fma(vel, ti, ck[k]), vx1 = fma(vel, ti, ck[k + 1]);
                     qmin = min(qmin, min(__double2hiint(fma(vx0, vx0, b2)), __double2hiint(fma(vx1, vx1, b2))));
                 }
                 if (S & 1) {
-                    const double vx = fma(vel, row[S - 1], nvtc);
+                    const double vx = fma(vel, ti, ck[S - 1]);
                     qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
                 }
             } else {
+                const double* row = sm.ftab[buf] + i * SP;
                 for (int k = 0; k < Sx; ++k) {
                     const double vx = fma(vel, row[k], nvtc);
                     qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));

@@ -81,11 +81,14 @@ __device__ __forceinline__ WalkerConsts make_walker_consts(const double* par, in
     // rounding slack: q_fma and q_faithful differ by < 2 ulp, sqrt rounds by 1/2 ulp
     w.qthr = (w.q.p == 0.0) ? -1.0 : (w.q.onep * w.q.onep) * (1.0 + 16 * kEps);
     w.fbar = (w.q.fout == 1.0) ? 1.0 : bin_mean_const(w.q.fout, S);
-    // one-FMA position vx' = vel*ft - vel*tcen: |vx' - vx| <= eps*|vel*tcen| + 3 eps |vx'|, hence
-    // q' > (eps|vtc| + sqrt(eps^2 vtc^2 + (1+p)^2))^2 (1 + O(eps))  =>  the faithful z exceeds 1+p
+    // sweep position vx' = fma(vel, t_i, ck), ck = fma(vel, off_k, -vel*tcen): against the reference's
+    // vx = fl(vel * fl(fl(t_i + off_k) - tcen)) it carries the rounding of ck, of the final fma and of
+    // the reference's own ft and x:  |vx' - vx| <= 2 eps (|vel tcen| + |vel| off_k) + 3 eps |vx'|
+    // (off_k < one cadence < 1 day), hence
+    // q' > (e + sqrt(e^2 + (1+p)^2))^2 (1 + O(eps))  =>  the faithful z exceeds 1+p
     const double vtc = w.vel * w.tcen;
     w.nvtc = -vtc;
-    const double ev = kEps * fabs(vtc);
+    const double ev = kEps * (2 * fabs(vtc) + 2 * fabs(w.vel));
     const double u = (ev + ::sqrt(ev * ev + w.q.onep * w.q.onep)) * (1.0 + 32 * kEps);
     w.qthr_c = (w.q.p == 0.0) ? -1.0 : u * u * (1.0 + 8 * kEps);
     // q' >= 0 for finite inputs, so its IEEE bit pattern orders like an integer
