@@ -189,7 +189,7 @@ def cpu_reference_rate(wl, budget_s, pool, cores, nwalk=None):
     pool.map(_oracle_walker, [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(cores)])
     per_walker = (time.perf_counter() - t0)  # one walker per core, in parallel
     if nwalk is None:
-        nwalk = int(max(cores, min(4 * W, budget_s / max(per_walker, 1e-6) * cores)))
+        nwalk = int(max(cores, min(64 * W, budget_s / max(per_walker, 1e-6) * cores)))
     jobs = [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(nwalk)]
     t0 = time.perf_counter()
     pool.map(_oracle_walker, jobs, chunksize=max(1, nwalk // (cores * 4)))
