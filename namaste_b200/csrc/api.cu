@@ -388,6 +388,7 @@ template <int S>
 int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     if (dtype == NMB_F32) return launch_eval_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (dtype != NMB_F64_STRICT) return launch_eval_mb<S, 4, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
     static const int minb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 4;
     if (minb == 5) return launch_eval_mb<S, 5, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (minb == 6) return launch_eval_mb<S, 6, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
@@ -452,6 +453,45 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     return rc;
 }
 
+template <int S, int PATH, int THREADS>
+int launch_direct_t(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                    cudaStream_t st, const nmb::SampleCtx& sc, int* resident_out) {
+    auto kern = nmb::window_direct_kernel<S, THREADS, 512 / THREADS, PATH>;
+    const size_t smem = sizeof(nmb::DirectSmem<THREADS>);
+    static thread_local int resident = 0;
+    if (!resident) {
+        if (int rc = set_smem(kern, smem)) return rc;
+        int dev = 0, sms = 0, per_sm = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+        resident = sms * std::max(per_sm, 1);
+    }
+    if (resident_out) { *resident_out = resident; if (!params && !sc.enabled) return NMB_OK; }
+    const size_t CW = (size_t)lc->ncand * W;
+    CU(launch_pdl(kern, dim3((unsigned)CW), dim3(THREADS), smem, st, lc->view(), params, W, priors, lc->ws, lnprob,
+                  loglike, sc));
+    g_launches++;
+    return NMB_OK;
+}
+
+// A block per walker: four warps (one slot each for a K2 transit) while the ensemble fits one resident
+// wave, two warps per walker (twice the blocks per SM) beyond that.
+template <int S, int PATH>
+int launch_direct(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                  cudaStream_t st, const nmb::SampleCtx& sc) {
+    static const int force = std::getenv("NMB_DIRECT_THREADS") ? std::atoi(std::getenv("NMB_DIRECT_THREADS")) : 0;
+    static thread_local int resident128 = 0;
+    if (!resident128) {
+        if (int rc = launch_direct_t<S, PATH, 128>(lc, nullptr, W, priors, lnprob, loglike, st, nmb::SampleCtx{}, &resident128))
+            return rc;
+    }
+    const size_t CW = (size_t)lc->ncand * W;
+    const bool wide = force ? force == 128 : CW <= (size_t)resident128;
+    return wide ? launch_direct_t<S, PATH, 128>(lc, params, W, priors, lnprob, loglike, st, sc, nullptr)
+                : launch_direct_t<S, PATH, 64>(lc, params, W, priors, lnprob, loglike, st, sc, nullptr);
+}
+
 template <int S>
 int launch_window(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                   cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
@@ -459,9 +499,19 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
     constexpr int kWinThreads = 64;
     lc->timer.mark(0, st);
-    CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),
-                  dim3(kWinThreads), 0, st, lc->view(), params, W, priors, lc->ws, lnprob, loglike, sc));
-    g_launches++;
+    // a block per walker evaluates short ranges on the spot (window_direct_kernel); the thread-per-walker
+    // kernel that only fills the queue remains for the GP model mode and as NMB_NO_DIRECT=1
+    static const bool no_direct = std::getenv("NMB_NO_DIRECT") != nullptr;
+    if (!no_direct && !lc->ws.modelbuf) {
+        int rc = dtype == NMB_F32          ? launch_direct<S, 2>(lc, params, W, priors, lnprob, loglike, st, sc)
+                 : dtype == NMB_F64_STRICT ? launch_direct<S, 1>(lc, params, W, priors, lnprob, loglike, st, sc)
+                                           : launch_direct<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+        if (rc) return rc;
+    } else {
+        CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),
+                      dim3(kWinThreads), 0, st, lc->view(), params, W, priors, lc->ws, lnprob, loglike, sc));
+        g_launches++;
+    }
     lc->timer.mark(1, st);
     const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     lc->timer.mark(2, st);
@@ -532,7 +582,8 @@ static int lnprob_impl(nmb_lc* lc, const double* params, int64_t W, const double
                        double* loglike, int mode, int dtype, void* stream, const nmb::SampleCtx& sc) {
     if (!lc || !params || (!lnprob && !sc.enabled)) return fail(NMB_ERR_ARG, "nmb_lnprob: null pointer");
     if (W < 1 || W > (1 << 24)) return fail(NMB_ERR_ARG, "nmb_lnprob: W out of range");
-    if (dtype != NMB_F64 && dtype != NMB_F32) return fail(NMB_ERR_ARG, "nmb_lnprob: dtype must be NMB_F64 or NMB_F32");
+    if (dtype != NMB_F64 && dtype != NMB_F32 && dtype != NMB_F64_STRICT)
+        return fail(NMB_ERR_ARG, "nmb_lnprob: dtype must be NMB_F64, NMB_F64_STRICT or NMB_F32");
     if (dtype == NMB_F32 && mode == NMB_MODE_FUSED) return fail(NMB_ERR_ARG, "nmb_lnprob: NMB_MODE_FUSED is FP64 only");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = NMB_OK;

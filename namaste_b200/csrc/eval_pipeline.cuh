@@ -364,6 +364,75 @@ __device__ __forceinline__ int bsearch_t(const double* __restrict__ t, int n, do
     return lo;
 }
 
+// chi^2 of the timestamps outside [ilo, ihi): pre[ilo] + (pre[n] - pre[ihi]) in double-double.  The six
+// prefix-sum words are loaded by the constructor and combined by value(), so a caller can issue the loads
+// early and pay their latency under other work.
+struct window_oot {
+    double hn, hh, hl, ln, lh, ll;
+    __device__ __forceinline__ window_oot(const LcView& lc, int cand, int ilo, int ihi) {
+        const int n = (int)lc.n[cand];
+        const double* ph = lc.pre_hi + (long long)cand * (lc.npad + 1);
+        const double* pl = lc.pre_lo + (long long)cand * (lc.npad + 1);
+        hn = ph[n]; hh = ph[ihi]; hl = ph[ilo];
+        ln = pl[n]; lh = pl[ihi]; ll = pl[ilo];
+    }
+    __device__ __forceinline__ double value() const {
+        double sa, ea, sb, eb;
+        two_sum(hn, -hh, sa, ea);
+        ea += ln - lh;
+        two_sum(sa, hl, sb, eb);
+        eb += ea + ll;
+        return sb + eb;
+    }
+};
+
+// Conservative in-transit index range [ilo, ihi) of one walker from the geometry (O(1): two lookups in
+// the uniform time grid) and the chi^2 of everything outside it from the double-double prefix sums.
+// Exact: the range is a superset of the in-transit timestamps and stage 2 classifies every sample.
+__device__ __forceinline__ void walker_range(const LcView& lc, int cand, const WalkerConsts& wc, int Sx, int& ilo,
+                                             int& ihi) {
+    const int n = (int)lc.n[cand];
+    const double span = lc.off[(long long)cand * Sx + Sx - 1];
+    const double hx2 = wc.qthr - wc.b2;
+    bool full = !(wc.fbar == 1.0);  // prefix sums assume the out-of-transit model is exactly 1
+    bool empty = false;
+    double tlo = 0.0, thi = 0.0;
+    if (!full) {
+        if (hx2 < 0.0) {
+            empty = true;  // |b| beyond the limb: never in transit
+        } else if (!(hx2 >= 0.0) || !(fabs(wc.vel) > 0.0)) {
+            full = true;  // NaN somewhere, or vel == 0 (z == |b| for every sample)
+        } else {
+            const double ht = sqrt(hx2) / fabs(wc.vel) * (1.0 + 1e-9);
+            const double slack = 1e-9 * (fabs(wc.tcen) + 1.0) + fabs(span) * 1e-6;
+            tlo = wc.tcen - ht - span - slack;
+            thi = wc.tcen + ht + slack;
+            if (!(tlo == tlo) || !(thi == thi) || isinf(tlo) || isinf(thi)) full = true;
+        }
+    }
+    if (full) {
+        ilo = 0; ihi = n;
+    } else if (empty) {
+        ilo = 0; ihi = 0;
+    } else {
+        // O(1) lookup in the uniform time grid, widened by one cell on each side
+        const double t0 = lc.t0[cand], ginv = lc.ginv[cand];
+        const int gc = lc.gcount[cand];
+        const int* __restrict__ grid = lc.tgrid + (long long)cand * lc.gstride;
+        const double jl = floor((tlo - t0) * ginv) - 1.0, jh = floor((thi - t0) * ginv) + 2.0;
+        const int j0 = jl < 0.0 ? 0 : (jl > (double)gc ? gc : (int)jl);
+        const int j1 = jh < 0.0 ? 0 : (jh > (double)gc ? gc : (int)jh);
+        ilo = __ldg(grid + j0);
+        ihi = (jh > (double)gc) ? n : __ldg(grid + j1);
+        if (ihi < ilo) ihi = ilo;
+    }
+}
+__device__ __forceinline__ void walker_window(const LcView& lc, int cand, const WalkerConsts& wc, int Sx, int& ilo,
+                                              int& ihi, double& oot) {
+    walker_range(lc, cand, wc, Sx, ilo, ihi);
+    oot = window_oot(lc, cand, ilo, ihi).value();
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors,
@@ -379,57 +448,15 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
     if (tid == 0) trace_min(ws, 0);
     if (cw < CW) {
         const int cand = cw / W;
-        const int n = (int)lc.n[cand];
         const double* par = params;
         if (sc.enabled) {
             propose_stretch(sc, cand, cw % W, W);
             par = sc.q;  // the proposal just written by this thread (not through the read-only path)
         }
         const WalkerConsts wc = make_walker_consts(par + (long long)cw * 6, Sx);
-        const double span = lc.off[(long long)cand * Sx + Sx - 1];
-        const double hx2 = wc.qthr - wc.b2;
-        bool full = !(wc.fbar == 1.0);  // prefix sums assume the out-of-transit model is exactly 1
-        bool empty = false;
-        double tlo = 0.0, thi = 0.0;
-        if (!full) {
-            if (hx2 < 0.0) {
-                empty = true;  // |b| beyond the limb: never in transit
-            } else if (!(hx2 >= 0.0) || !(fabs(wc.vel) > 0.0)) {
-                full = true;  // NaN somewhere, or vel == 0 (z == |b| for every sample)
-            } else {
-                const double ht = sqrt(hx2) / fabs(wc.vel) * (1.0 + 1e-9);
-                const double slack = 1e-9 * (fabs(wc.tcen) + 1.0) + fabs(span) * 1e-6;
-                tlo = wc.tcen - ht - span - slack;
-                thi = wc.tcen + ht + slack;
-                if (!(tlo == tlo) || !(thi == thi) || isinf(tlo) || isinf(thi)) full = true;
-            }
-        }
         int ilo, ihi;
-        if (full) {
-            ilo = 0; ihi = n;
-        } else if (empty) {
-            ilo = 0; ihi = 0;
-        } else {
-            // O(1) lookup in the uniform time grid, widened by one cell on each side
-            const double t0 = lc.t0[cand], ginv = lc.ginv[cand];
-            const int gc = lc.gcount[cand];
-            const int* __restrict__ grid = lc.tgrid + (long long)cand * lc.gstride;
-            const double jl = floor((tlo - t0) * ginv) - 1.0, jh = floor((thi - t0) * ginv) + 2.0;
-            const int j0 = jl < 0.0 ? 0 : (jl > (double)gc ? gc : (int)jl);
-            const int j1 = jh < 0.0 ? 0 : (jh > (double)gc ? gc : (int)jh);
-            ilo = __ldg(grid + j0);
-            ihi = (jh > (double)gc) ? n : __ldg(grid + j1);
-            if (ihi < ilo) ihi = ilo;
-        }
-        // out-of-transit part: pre[ilo] + (pre[n] - pre[ihi]) in double-double
-        const double* ph = lc.pre_hi + (long long)cand * (lc.npad + 1);
-        const double* pl = lc.pre_lo + (long long)cand * (lc.npad + 1);
-        double sa, ea, sb, eb;
-        two_sum(ph[n], -ph[ihi], sa, ea);
-        ea += pl[n] - pl[ihi];
-        two_sum(sa, ph[ilo], sb, eb);
-        eb += ea + pl[ilo];
-        const double oot = sb + eb;
+        double oot;
+        walker_window(lc, cand, wc, Sx, ilo, ihi, oot);
         if (ihi - ilo <= 0) {  // never in transit: done here (the GP solve reads the idle range instead)
             if (!ws.modelbuf) {
                 const double lp = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
@@ -465,7 +492,8 @@ constexpr int kEvalPass = NMB_EVALPASS;  // supersamples of one slot (the unit o
 #endif
 constexpr int kEvalMerge = NMB_EVALMERGE;  // most consecutive slots of a walker a warp evaluates in one pass
 
-// PATH: 0 = general IEEE FP64, 1 = FP64 hot path (default), 2 = FP32 hot path (NMB_F32)
+// PATH: 0 = general IEEE FP64, 1 = FP64 hot path in the reference's rounding sequence (NMB_F64_STRICT),
+//       2 = FP32 hot path (NMB_F32), 3 = relaxed FP64 hot path (NMB_F64, the default)
 template <int PATH>
 __device__ __forceinline__ double sample_flux_eval(double ti, double offk, const WalkerConsts& wc,
                                                    const QuadConstsF& cf, const QuadConsts* gq);
@@ -487,6 +515,24 @@ __device__ __forceinline__ double sample_flux_eval<1>(double ti, double offk, co
     // hot cases with branch-free Newton-Raphson quotients/roots; anything else (other cases,
     // operands outside the normal range -> non-finite z or F) takes the general IEEE path
     if (!occultquad_hot(z, wc.q, F) || !(fabs(F) <= 1e300)) {
+        const double zz = ::sqrt(q);
+        F = (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, gq);
+    }
+    return F;
+}
+template <>
+__device__ __forceinline__ double sample_flux_eval<3>(double ti, double offk, const WalkerConsts& wc,
+                                                      const QuadConstsF&, const QuadConsts* gq) {
+    // geometry exactly as in the strict path (z is the correctly rounded root, so the case a sample
+    // falls in is the reference's); only the occultation arithmetic is relaxed
+    const double ft = ti + offk;
+    const double x = ft - wc.tcen;
+    const double vx = wc.vel * x;
+    const double q = wc.b2 + vx * vx;
+    const double z = FastOps::sqrt(q);
+    if (z > wc.q.onep) return wc.q.fout;
+    double F;
+    if (!occultquad_relaxed(z, wc.q, F) || !(fabs(F) <= 1e300)) {
         const double zz = ::sqrt(q);
         F = (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, gq);
     }
@@ -717,6 +763,162 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
             ws.counters[1] = 0;
             ws.counters[2] = 0;
             ws.counters[3] = 0;
+        }
+    }
+}
+
+// ---- windowed mode, direct evaluation: one thread block per walker ------------------------------
+// For small and medium ensembles the two-kernel pipeline is a chain of dependent global-memory round
+// trips (ranges -> queue tail -> slot records -> walker constants -> partials -> completion count),
+// each ~1 us, around a few microseconds of arithmetic.  Here a block does everything for its walker
+// without leaving the SM: every thread derives the walker's constants and window (uniform work, no
+// exchange needed), each of the block's warps evaluates one pass of up to `merge` slots, the slot
+// partials meet in shared memory and warp 0 folds them, adds the priors and finishes the walker
+// (lnprob store or the sampler's accept step).  Slot boundaries, the summation order inside a slot
+// and the fold over slots are those of eval_slots_kernel, so the result has the same bits.  Walkers
+// whose range needs more than one pass per warp (slow or grazing walkers; every walker of the long
+// light curves) are pushed to the slot queue and evaluated by eval_slots_kernel, launched behind
+// this kernel as before.
+template <int THREADS>
+struct DirectSmem {
+    double scratch[THREADS / 32][kEvalMerge * (2 * kEvalPass + 8) + kEvalMerge * kEvalPass];
+    WalkerConsts wc[THREADS / 32];
+    double part[(THREADS / 32) * kEvalMerge];
+    int first;
+};
+
+template <int S, int THREADS, int MINB, int PATH>
+__global__ void __launch_bounds__(THREADS, MINB)
+window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
+                     double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
+    constexpr int NWARP = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DirectSmem<THREADS>& sm = *reinterpret_cast<DirectSmem<THREADS>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cw = blockIdx.x;
+    const int cand = cw / W;
+    const int Sx = s_of<S>(lc.S);
+    const int SP = Sx | 1;
+    const int TSW = ws.tsw;
+    // the finishing warp's row of the prior table does not depend on the previous kernel: load it first
+    double pr_lo = 0.0, pr_hi = 0.0, pr_kind = 0.0, pr_mu = 0.0, pr_sg = 1.0;
+    if (priors && warp == 0 && lane < 6) {
+        const double* row = priors + (long long)cand * 36 + lane * 6;
+        pr_lo = __ldg(row); pr_hi = __ldg(row + 1); pr_kind = __ldg(row + 2); pr_mu = __ldg(row + 3); pr_sg = __ldg(row + 4);
+    }
+    pdl_wait();     // walker positions come from the previous kernel
+    pdl_trigger();  // eval_slots_kernel may be scheduled; it waits for this grid to finish before reading
+    if (tid == 0) trace_min(ws, 0);
+
+    double p6[6];
+    if (sc.enabled) {
+        const Proposal pr = propose_compute(sc, cand, cw % W);  // a pure function: every thread gets the same
+        if (tid == 0) propose_store(sc, pr, cand, cw % W, W);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) p6[d] = pr.q[d];
+    } else {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) p6[d] = __ldg(params + (long long)cw * 6 + d);
+    }
+    double x_lane = 0.0;  // lane d of the finishing warp keeps parameter d for the priors
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+        if (lane == d) x_lane = p6[d];
+    const WalkerConsts wcr = make_walker_consts(p6, Sx);
+    int ilo, ihi;
+    walker_range(lc, cand, wcr, Sx, ilo, ihi);
+    int pps;
+    const int nsl = slots_for(ihi - ilo, TSW, ws.maxslots, pps);
+    // out-of-transit chi^2: the loads go out now, the finishing warp combines them after its pass
+    const window_oot oot_words(lc, cand, warp == 0 ? ilo : 0, warp == 0 ? ihi : 0);
+
+    // priors of the walker, one parameter per lane of warp 0, summed in the reference's order
+    auto ln_prior_w0 = [&]() {
+        if (!priors) return 0.0;
+        double wall = 0.0, bump = 0.0;
+        if (lane < 6) ln_prior_terms_v(x_lane, pr_lo, pr_hi, (int)pr_kind, pr_mu, pr_sg, wall, bump);
+        double lp = 0.0;
+        for (int n = 0; n < 6; ++n) lp = (lp - __shfl_sync(0xffffffffu, wall, n)) + __shfl_sync(0xffffffffu, bump, n);
+        return lp;
+    };
+
+    if (nsl == 0) {  // never in transit
+        if (warp == 0) {
+            const double lp = ln_prior_w0();
+            if (lane == 0) finish_walker(sc, cw, W, oot_words.value(), lp, lnprob, loglike);
+        }
+        if (tid == 0) trace_max(ws, 3);
+        return;
+    }
+    if (pps > 1 || nsl > NWARP * ws.merge) {  // more than one pass per warp: onto the queue
+        if (tid == 0) {
+            sm.first = atomicAdd(ws.counters + 1, nsl);
+            ws.oot[cw] = oot_words.value();
+            ws.wcs[cw] = wcr;
+            ws.rlo[cw] = ilo;
+            ws.rhi[cw] = ihi;
+            ws.nslots[cw] = nsl;
+        }
+        __syncthreads();
+        const int first = sm.first, step = pps * TSW;
+        for (int i = tid; i < nsl; i += THREADS) {
+            SlotRec r;
+            r.cw = cw; r.t0 = ilo + i * step; r.t1 = min(ihi, ilo + (i + 1) * step); r.first = first;
+            *reinterpret_cast<int4*>(ws.slots + first + i) = *reinterpret_cast<const int4*>(&r);
+        }
+        if (tid == 0) trace_max(ws, 3);
+        return;
+    }
+
+    // ---- direct: warp w takes the consecutive slots [w * per, (w + 1) * per) as one pass
+    WalkerConsts& wc = sm.wc[warp];
+    if (lane == 0) wc = wcr;
+    __syncwarp();
+    QuadConstsF cf = QuadConstsF{};
+    if (PATH == 2) cf = to_f32(wc.q);
+    const int per = (nsl + NWARP - 1) / NWARP;
+    const int s0 = warp * per, s1 = min(nsl, s0 + per);
+    if (s0 < s1) {
+        double* scratch = sm.scratch[warp];
+        double* terms = scratch + kEvalMerge * (2 * kEvalPass + 8);
+        const double* gt = lc.t + (long long)cand * lc.npad;
+        const double* gf = lc.f + (long long)cand * lc.npad;
+        const double* gw_ = lc.w + (long long)cand * lc.npad;
+        const double* goff = lc.off + (long long)cand * Sx;
+        const int t0 = ilo + s0 * TSW, tend = min(ihi, ilo + s1 * TSW);
+        const int nts = tend - t0;
+        const int nsamp = nts * Sx;
+        // flux and weight of the first 32 timestamps of the pass: requested before the flux rounds
+        const double f_pre = lane < nts ? __ldg(gf + t0 + lane) : 0.0;
+        const double w_pre = lane < nts ? __ldg(gw_ + t0 + lane) : 0.0;
+        for (int j = lane; j < nsamp; j += 32) {
+            const int h = j / Sx, k = j - h * Sx;
+            scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + t0 + h), __ldg(goff + k), wc, cf, &wc.q);
+        }
+        __syncwarp();
+        for (int h = lane; h < nts; h += 32) {
+            const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + h * SP) : bin_mean_rt(scratch + h * SP, Sx);
+            const double r = (h == lane ? f_pre : __ldg(gf + t0 + h)) - m;
+            terms[h] = (h == lane ? w_pre : __ldg(gw_ + t0 + h)) * (r * r);
+        }
+        __syncwarp();
+        for (int q = 0; q < s1 - s0; ++q) {
+            const int b0 = q * TSW, nq = min(TSW, nts - b0);
+            double acc = 0.0;
+            for (int h = lane; h < nq; h += 32) acc += terms[b0 + h];
+            acc = warp_sum(acc);
+            if (lane == 0) sm.part[s0 + q] = acc;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double ssum = 0.0;
+        for (int c = lane; c < nsl; c += 32) ssum += sm.part[c];
+        ssum = warp_sum(ssum);
+        const double lp = ln_prior_w0();
+        if (lane == 0) {
+            finish_walker(sc, cw, W, oot_words.value() + ssum, lp, lnprob, loglike);
+            trace_max(ws, 3);
         }
     }
 }

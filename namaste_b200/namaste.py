@@ -332,7 +332,9 @@ def Optimize_mono(flatlc, priors, starts, tcen=None, tdur=None, monomodel=None, 
     starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
     oversamp = getattr(monomodel, "oversamp", 10) if monomodel is not None else 10
     staged = stage_lightcurve(flatlc, oversamp)
-    batch = _BatchedObjective(lambda rows: -1 * staged.lnprob(rows, priors, mode=mode), len(starts))
+    # forward differences with a 1e-8 step see the rounding of the objective: evaluate it in the reference's
+    # own rounding sequence (dtype "strict"), so the optimisers walk the surface the reference's would
+    batch = _BatchedObjective(lambda rows: -1 * staged.lnprob(rows, priors, mode=mode, dtype="strict"), len(starts))
     results = [None] * len(starts)
 
     def run(i):

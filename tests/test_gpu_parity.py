@@ -1,9 +1,11 @@
 """GPU parity tests: the CUDA path (through the C ABI) against fixtures produced by the
 reference's own code (tests/golden, see oracle/gen_golden.py) and against the oracle.
 
-Tolerances: BASELINE.json north_star asks for 1e-10 relative on lnprob in FP64; the
-element-level checks are much tighter because the kernels keep the reference's operation
-order (differences come only from libm and from per-element Bulirsch convergence)."""
+Tolerances: BASELINE.json north_star asks for 1e-10 relative on lnprob in FP64.  Two FP64
+arithmetic variants are tested: dtype "strict" keeps the reference's operation order
+(differences come only from libm and from per-element Bulirsch convergence) and is held to
+2e-13; the default dtype "f64" contracts multiply-adds and uses <= 1.5-ulp quotients / roots
+in the two hot occultation cases (measured <= 1e-13 on every fixture) and is held to 2e-12."""
 import numpy as np
 import pytest
 
@@ -12,7 +14,9 @@ from conftest import load_golden, priors_from_table
 pytestmark = pytest.mark.gpu
 
 LNPROB_RTOL = 1e-10   # north-star tolerance
-LNPROB_RTOL_TIGHT = 2e-13  # what the implementation actually achieves (regression guard)
+LNPROB_RTOL_TIGHT = 2e-13  # what dtype="strict" actually achieves (regression guard)
+LNPROB_RTOL_DEFAULT = 2e-12  # regression guard for the default dtype="f64" (relaxed arithmetic)
+GUARD = {"f64": LNPROB_RTOL_DEFAULT, "strict": LNPROB_RTOL_TIGHT}
 FP32_RTOL = 2e-4  # measured 0.8e-5 .. 9.3e-5 (the lambda_d combination cancels ~60x)
 
 
@@ -55,34 +59,40 @@ def test_occultquad_all_cases(nb):
     print("occultquad worst abs deviation:", worst)
 
 
+@pytest.mark.parametrize("dtype", ["f64", "strict"])
 @pytest.mark.parametrize("mode", ["brute", "windowed", "fused"])
-def test_logged_known_answers(nb, mode):
+def test_logged_known_answers(nb, mode, dtype):
+    if mode == "fused" and dtype != "strict":
+        pytest.skip("the single-launch diagnostic kernel has one arithmetic (strict)")
     g = load_golden("kat_epic203311200")
     pri = priors_from_table(g["priors"])
     model = nb.MonotransitModel(*g["params"][0])
     for th, nll, ll, lp in zip(g["params"], g["nll_logged"], g["ll"], g["lp"]):
-        got = nb.MonoOnlyNegLogProb(th, g["lc"], pri, model, mode=mode)
+        got = nb.MonoOnlyNegLogProb(th, g["lc"], pri, model, mode=mode, dtype=dtype)
         assert abs(got - nll) / nll < 5e-11          # vs the value the reference logged in 2018
-        assert abs(got + (ll + lp)) / nll < LNPROB_RTOL_TIGHT  # vs the reference run here on the same lc
+        assert abs(got + (ll + lp)) / nll < GUARD[dtype]  # vs the reference run here on the same lc
     assert np.array_equal(model.get_parameter_vector(), g["params"][-1])
 
 
 @pytest.mark.parametrize("name", ["config1_epic203311200", "synth_k2_s11", "synth_kepler_s15",
                                   "synth_tess_s10", "synth_tess_s1"])
+@pytest.mark.parametrize("dtype", ["f64", "strict"])
 @pytest.mark.parametrize("mode", ["brute", "windowed", "fused"])
-def test_lnprob_fixtures(nb, name, mode):
+def test_lnprob_fixtures(nb, name, mode, dtype):
+    if mode == "fused" and dtype != "strict":
+        pytest.skip("the single-launch diagnostic kernel has one arithmetic (strict)")
     g = load_golden(name)
     S = int(g["oversamp"]) if "oversamp" in g.files else 10
     lc = nb.LightCurve(g["lc"], oversamp=S)
-    lnp, ll = lc.lnprob(g["walkers"], g["priors"], mode=mode, return_loglike=True)
+    lnp, ll = lc.lnprob(g["walkers"], g["priors"], mode=mode, return_loglike=True, dtype=dtype)
     ref_ll, ref_lp = g["ll"], g["lp"]
     finite = np.isfinite(ref_ll + ref_lp)
     assert np.array_equal(np.isfinite(lnp), finite)
     r_ll = rel(ll[finite], ref_ll[finite]).max()
     r_lnp = rel(lnp[finite], (ref_ll + ref_lp)[finite]).max()
-    print(name, mode, "max rel ll", r_ll, "lnprob", r_lnp)
+    print(name, mode, dtype, "max rel ll", r_ll, "lnprob", r_lnp)
     assert r_ll < LNPROB_RTOL and r_lnp < LNPROB_RTOL
-    assert r_ll < LNPROB_RTOL_TIGHT and r_lnp < LNPROB_RTOL_TIGHT
+    assert r_ll < GUARD[dtype] and r_lnp < GUARD[dtype]
     lc.close()
 
 
@@ -131,9 +141,10 @@ def test_brute_vs_windowed_vs_oracle_random_box(nb):
     ref = o.lnprob_ensemble(pos, lc, pri)
     staged = nb.LightCurve(lc, oversamp=10)
     for mode in ("brute", "windowed", "fused"):
-        got = staged.lnprob(pos, pri, mode=mode)
-        assert rel(got, ref).max() < LNPROB_RTOL_TIGHT, mode
-    assert np.allclose(nb.MonoOnlyLogProb(pos, lc, pri), ref, rtol=LNPROB_RTOL_TIGHT, atol=0)
+        for dtype in ("f64", "strict"):
+            got = staged.lnprob(pos, pri, mode=mode, dtype=dtype)
+            assert rel(got, ref).max() < GUARD[dtype], (mode, dtype)
+    assert np.allclose(nb.MonoOnlyLogProb(pos, lc, pri), ref, rtol=LNPROB_RTOL_DEFAULT, atol=0)
 
 
 def test_errors_are_loud(nb):
@@ -192,7 +203,7 @@ def test_degenerate_limb_darkening_matches_oracle(nb):
         assert np.array_equal(np.isnan(got), np.isnan(ref)), (mode, got, ref)
         ok = np.isfinite(ref)
         assert np.array_equal(np.isinf(got), np.isinf(ref)), (mode, got, ref)
-        assert rel(got[ok], ref[ok]).max() < LNPROB_RTOL_TIGHT, mode
+        assert rel(got[ok], ref[ok]).max() < LNPROB_RTOL_DEFAULT, mode
     staged.close()
 
 

@@ -36,9 +36,9 @@ def test_chain_matches_cpu_oracle_draw_by_draw(nb, mode):
     # proposals are bit-identical as long as the accept decisions agree; they can only differ when
     # |lnpdiff - ln u| ~ 1e-12, which a 25-step chain does not hit
     assert np.array_equal(s.chain, ref_chain)
-    assert np.allclose(s.lnprobability, ref_ln, rtol=1e-12, atol=0)
+    assert np.allclose(s.lnprobability, ref_ln, rtol=1e-11, atol=0)
     assert np.array_equal(s.naccepted, ref_acc)
-    assert np.array_equal(pos, ref_chain[:, -1, :]) and np.allclose(lnp, ref_ln[:, -1], rtol=1e-12)
+    assert np.array_equal(pos, ref_chain[:, -1, :]) and np.allclose(lnp, ref_ln[:, -1], rtol=1e-11)
     assert 0.1 < s.acceptance_fraction.mean() < 0.9
 
 
