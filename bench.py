@@ -313,21 +313,26 @@ def run_ours(args):
     ms_win = max_over_ranks(ms_win)
     ref_f64 = out.cpu().numpy().copy()
     # FP32 variant (reported separately): windowed stage 1 + FP32 transit model in stage 2
-    def device_loop_f32(steps):
+    def device_loop_dtype(steps, dtype, mode="windowed"):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         torch.cuda.synchronize()
         for e0, e1 in evs:
             flush.zero_()
             e0.record(stream)
-            staged.lnprob_device(d_pos, d_pri, out=out, mode="windowed", dtype="f32")
+            staged.lnprob_device(d_pos, d_pri, out=out, mode=mode, dtype=dtype)
             e1.record(stream)
         torch.cuda.synchronize()
         return sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    device_loop_f32(max(args.warmup, 3))
-    ms_f32 = max_over_ranks(device_loop_f32(args.steps))
-    f32_out = out.cpu().numpy().copy()
     fin = np.isfinite(ref_f64) & (np.abs(ref_f64) < 1e15)
+    device_loop_dtype(max(args.warmup, 3), "f32")
+    ms_f32 = max_over_ranks(device_loop_dtype(args.steps, "f32"))
+    f32_out = out.cpu().numpy().copy()
     f32_err = float(np.max(np.abs(f32_out[fin] - ref_f64[fin]) / np.abs(ref_f64[fin])))
+    # strict variant (the reference's own rounding sequence in the hot occultation cases), brute force
+    device_loop_dtype(max(args.warmup, 3), "strict", "brute")
+    ms_strict = max_over_ranks(device_loop_dtype(args.steps, "strict", "brute"))
+    strict_out = out.cpu().numpy().copy()
+    strict_diff = float(np.max(np.abs(strict_out[fin] - ref_f64[fin]) / np.abs(ref_f64[fin])))
     staged.lnprob_device(d_pos, d_pri, out=out, mode="windowed")  # leave the FP64 result in `out`
     ref_out = out.cpu().numpy().copy()
 
@@ -459,6 +464,11 @@ def run_ours(args):
         "fp32": {"value": units / (ms_f32 / args.steps * 1e-3), "unit": "wt/s", "ms_per_step": ms_f32 / args.steps,
                  "max_rel_err_vs_fp64": f32_err,
                  "note": "NMB_F32: FP32 transit model (depth space) in the windowed pipeline; reported separately"},
+        "strict": {"value": W * N * world * args.steps / (ms_strict * 1e-3), "unit": "wt/s", "ms_per_step": ms_strict / args.steps,
+                   "max_rel_diff_default_vs_strict": strict_diff,
+                   "note": "NMB_F64_STRICT, brute force: the hot occultation cases in the reference's own rounding sequence "
+                           "(bit-identical to NumPy in most elements); the default NMB_F64 contracts multiply-adds and uses "
+                           "<= 1.5-ulp quotients / roots there (lnprob within 1e-13 of the reference, tolerance 1e-10)"},
         "walker_split": split,
         "gp": {"value": units / (ms_gp * 1e-3), "unit": "wt/s", "ms_per_step": ms_gp, "ndim": 8,
                "note": "MonoLogProb: celerite RealTerm + jitter with the transit model as mean (2 free kernel "

@@ -388,8 +388,13 @@ template <int S>
 int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     if (dtype == NMB_F32) return launch_eval_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
-    if (dtype != NMB_F64_STRICT) return launch_eval_mb<S, 4, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
-    static const int minb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 4;
+    static const int minb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 0;
+    if (dtype != NMB_F64_STRICT) {
+        // five blocks (20 warps) per SM: the relaxed path fits 96 registers with two spilled words, and the
+        // shorter per-warp share of the queue outweighs them (measured: -4 % ... -7 % on every workload)
+        if (minb == 4) return launch_eval_mb<S, 4, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+        return launch_eval_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+    }
     if (minb == 5) return launch_eval_mb<S, 5, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (minb == 6) return launch_eval_mb<S, 6, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
     return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
@@ -475,21 +480,24 @@ int launch_direct_t(nmb_lc* lc, const double* params, int W, const double* prior
     return NMB_OK;
 }
 
-// A block per walker: four warps (one slot each for a K2 transit) while the ensemble fits one resident
-// wave, two warps per walker (twice the blocks per SM) beyond that.
+// A block of four warps per walker (one slot per warp for a K2 transit).  Used while the ensemble fits one
+// resident wave of such blocks: beyond that the walkers left to the queue would wait for several waves of
+// direct blocks, and the two-kernel pipeline balances better (measured: 1024 walkers of BASELINE config 2,
+// 58 us direct against 50 us through the queue; 512-walker half-steps 24 us against 34 us).
+// *use = false tells the caller to take the queue path.
 template <int S, int PATH>
 int launch_direct(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                  cudaStream_t st, const nmb::SampleCtx& sc) {
-    static const int force = std::getenv("NMB_DIRECT_THREADS") ? std::atoi(std::getenv("NMB_DIRECT_THREADS")) : 0;
-    static thread_local int resident128 = 0;
-    if (!resident128) {
-        if (int rc = launch_direct_t<S, PATH, 128>(lc, nullptr, W, priors, lnprob, loglike, st, nmb::SampleCtx{}, &resident128))
+                  cudaStream_t st, const nmb::SampleCtx& sc, bool* use) {
+    static const int force = std::getenv("NMB_DIRECT") ? std::atoi(std::getenv("NMB_DIRECT")) : -1;
+    static thread_local int resident = 0;
+    if (!resident) {
+        if (int rc = launch_direct_t<S, PATH, 128>(lc, nullptr, W, priors, lnprob, loglike, st, nmb::SampleCtx{}, &resident))
             return rc;
     }
     const size_t CW = (size_t)lc->ncand * W;
-    const bool wide = force ? force == 128 : CW <= (size_t)resident128;
-    return wide ? launch_direct_t<S, PATH, 128>(lc, params, W, priors, lnprob, loglike, st, sc, nullptr)
-                : launch_direct_t<S, PATH, 64>(lc, params, W, priors, lnprob, loglike, st, sc, nullptr);
+    *use = force >= 0 ? force != 0 : CW <= (size_t)resident;
+    if (!*use) return NMB_OK;
+    return launch_direct_t<S, PATH, 128>(lc, params, W, priors, lnprob, loglike, st, sc, nullptr);
 }
 
 template <int S>
@@ -499,15 +507,16 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
     constexpr int kWinThreads = 64;
     lc->timer.mark(0, st);
-    // a block per walker evaluates short ranges on the spot (window_direct_kernel); the thread-per-walker
-    // kernel that only fills the queue remains for the GP model mode and as NMB_NO_DIRECT=1
-    static const bool no_direct = std::getenv("NMB_NO_DIRECT") != nullptr;
-    if (!no_direct && !lc->ws.modelbuf) {
-        int rc = dtype == NMB_F32          ? launch_direct<S, 2>(lc, params, W, priors, lnprob, loglike, st, sc)
-                 : dtype == NMB_F64_STRICT ? launch_direct<S, 1>(lc, params, W, priors, lnprob, loglike, st, sc)
-                                           : launch_direct<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+    // small ensembles: a block per walker evaluates short ranges on the spot (window_direct_kernel); otherwise,
+    // and in the GP model mode, the thread-per-walker kernel fills the queue for eval_slots_kernel
+    bool direct = false;
+    if (!lc->ws.modelbuf) {
+        int rc = dtype == NMB_F32          ? launch_direct<S, 2>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
+                 : dtype == NMB_F64_STRICT ? launch_direct<S, 1>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
+                                           : launch_direct<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc, &direct);
         if (rc) return rc;
-    } else {
+    }
+    if (!direct) {
         CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),
                       dim3(kWinThreads), 0, st, lc->view(), params, W, priors, lc->ws, lnprob, loglike, sc));
         g_launches++;

@@ -75,6 +75,10 @@ __device__ __forceinline__ void trace_max(const EvalWs& ws, int slot) {
     if (ws.trace) atomicMax(ws.trace + slot, gtimer());
 }
 
+// line prefetch into L1 (no register, no dependency): used where an address is known several dependent
+// global round trips before its data is needed
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Every evaluated walker ends here exactly once: plain evaluation writes the outputs, sampler mode
 // runs the accept/reject step of the stretch move instead.
 __device__ __forceinline__ void finish_walker(const SampleCtx& sc, long long cw, int W, double ll, double lp,
@@ -604,7 +608,7 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
         ch_nxt = __shfl_sync(0xffffffffu, ch_nxt, 0);
     }
 
-    int cur_cw = -1, cur_first = 0, seg = 0, cand = 0;
+    int cur_cw = -1, cur_first = 0, seg = 0, cand = 0, cur_nsl = 0;
     WalkerConsts& wc = sm.wc[warp];
     QuadConstsF cf = QuadConstsF{};
     const double *gt = nullptr, *gf = nullptr, *gw_ = nullptr, *goff = nullptr;
@@ -615,7 +619,7 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
     auto leave_walker = [&]() {
         if (cur_cw < 0 || ws.modelbuf) return;
         int done = 0;
-        const int nsl = __ldcg(ws.nslots + cur_cw);
+        const int nsl = cur_nsl;
         if (lane == 0 && seg < nsl) {
             __threadfence();
             done = atomicAdd(ws.slotsdone + cur_cw, seg);
@@ -654,12 +658,21 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
         const int cw0 = __shfl_sync(0xffffffffu, mine.cw, 0);
         const int t0 = __shfl_sync(0xffffffffu, mine.t0, 0);
         int tend = __shfl_sync(0xffffffffu, mine.t1, 0);
+        if (!ws.modelbuf) {
+            // the pass's time / flux / weight lines (<= 32 timestamps of them) start travelling now, under
+            // the fetch of the walker's constants and the flux rounds
+            const long long at = (long long)(cw0 / W) * lc.npad + min(t0 + lane, (int)lc.npad - 1);
+            prefetch_l1(lc.t + at);
+            prefetch_l1(lc.f + at);
+            prefetch_l1(lc.w + at);
+        }
         if (cw0 != cur_cw) {
             leave_walker();
             cur_cw = cw0;
             cur_first = __shfl_sync(0xffffffffu, mine.first, 0);
             seg = 0;
             cand = cur_cw / W;
+            cur_nsl = __ldcg(ws.nslots + cur_cw);  // needed when the walker is left: requested here
             {
                 static_assert(sizeof(WalkerConsts) % 8 == 0, "WalkerConsts is copied as doubles");
                 const double* src = reinterpret_cast<const double*>(ws.wcs + cur_cw);
