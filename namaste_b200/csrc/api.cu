@@ -400,6 +400,58 @@ int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, d
     return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
 
+// Stage 2 as one launch of queue workers + one direct block per walker (eval_mixed_kernel).
+template <int S, int MINB, int PATH>
+int launch_mixed_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                    cudaStream_t st, const nmb::SampleCtx& sc) {
+    auto kern = nmb::eval_mixed_kernel<S, kEvalThreads, MINB, PATH>;
+    const size_t smem = std::max(sizeof(nmb::EvalSmem<kEvalThreads>), sizeof(nmb::DirectSmem<kEvalThreads>));
+    static thread_local int sms = 0;
+    if (!sms) {
+        if (int rc = set_smem(kern, smem)) return rc;
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // queue workers: two blocks per SM (the queue only holds the long-range walkers; measured on BASELINE
+    // config 2: 57.7 us with one, 51.7 with two, 51.6 with three)
+    static const int nq_per_sm = std::getenv("NMB_MIXED_NQ") ? std::max(1, std::atoi(std::getenv("NMB_MIXED_NQ"))) : 2;
+    const int nq = sms * nq_per_sm;
+    const size_t CW = (size_t)lc->ncand * W;
+    CU(launch_pdl(kern, dim3((unsigned)(nq + CW)), dim3(kEvalThreads), smem, st, lc->view(), params, W, priors, lc->ws, sms,
+                  nq, lnprob, loglike, sc));
+    g_launches++;
+    return NMB_OK;
+}
+
+template <int S>
+int launch_mixed(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
+                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
+    if (dtype == NMB_F32) return launch_mixed_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (dtype == NMB_F64_STRICT) return launch_mixed_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
+    return launch_mixed_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+}
+
+// Ensembles between a few hundred walkers and about two resident waves of direct blocks take the mixed
+// stage 2: short ranges are evaluated by a block per walker, only long ranges are queued.  Below that the
+// queue alone already gives every slot its own warp (config 1, 100 walkers: 30.6 us against 31.9 us mixed);
+// above it the queue balances better than waves of blocks.  NMB_MIXED_MINCW / NMB_MIXED_MAXCW override.
+static bool use_mixed(const nmb_lc* lc, size_t CW) {
+    static const long long lo = std::getenv("NMB_MIXED_MINCW") ? std::atoll(std::getenv("NMB_MIXED_MINCW")) : 256;
+    static const long long hi = std::getenv("NMB_MIXED_MAXCW") ? std::atoll(std::getenv("NMB_MIXED_MAXCW")) : 1184;
+    return !lc->ws.modelbuf && (long long)CW >= lo && (long long)CW <= hi;
+}
+
+// Slots a direct block of eval_mixed_kernel takes: two per warp (six flux rounds).  A longer range in one
+// block would be the straggler of the launch (measured: three slots per warp = nine rounds, 13 us, against
+// 8 us for the rest) while queue workers run beside it and spread such walkers over the whole GPU.
+// window_direct_kernel takes one full pass per warp (`merge` slots): there the queue only starts after the
+// direct blocks, so fewer queued walkers is the better trade (config 1: 26.5 us against 32.7 us).
+static int direct_cap_slots(const nmb_lc* lc, bool queue_runs_beside) {
+    static const int per_warp = std::getenv("NMB_DIRECT_SLOTS") ? std::max(1, std::atoi(std::getenv("NMB_DIRECT_SLOTS"))) : 2;
+    return (kEvalThreads / 32) * (queue_runs_beside ? std::min(per_warp, lc->ws.merge) : lc->ws.merge);
+}
+
 template <int S, int THREADS, int MINB>
 int launch_sweep_t(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                    cudaStream_t st, const nmb::SampleCtx& sc) {
@@ -440,6 +492,8 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, lc->ngran, st)) return rc;
+    const bool mixed = use_mixed(lc, CW);
+    lc->ws.direct_cap = mixed ? direct_cap_slots(lc, true) : 0;
     lc->timer.mark(0, st);
     // 128-walker blocks when they alone fill the GPU, single-warp blocks (finer spread) otherwise
     static const int force_thr = std::getenv("NMB_SWEEP_THREADS") ? std::atoi(std::getenv("NMB_SWEEP_THREADS")) : 0;
@@ -452,7 +506,8 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
                          : launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (rc) return rc;
     lc->timer.mark(1, st);
-    rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
+    rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
+               : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     lc->timer.mark(2, st);
     lc->timer.done();
     return rc;
@@ -510,19 +565,23 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     // small ensembles: a block per walker evaluates short ranges on the spot (window_direct_kernel); otherwise,
     // and in the GP model mode, the thread-per-walker kernel fills the queue for eval_slots_kernel
     bool direct = false;
+    lc->ws.direct_cap = direct_cap_slots(lc, false);  // read by window_direct_kernel only (it never calls push_slots)
     if (!lc->ws.modelbuf) {
         int rc = dtype == NMB_F32          ? launch_direct<S, 2>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
                  : dtype == NMB_F64_STRICT ? launch_direct<S, 1>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
                                            : launch_direct<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc, &direct);
         if (rc) return rc;
     }
+    const bool mixed = !direct && use_mixed(lc, CW);
     if (!direct) {
+        lc->ws.direct_cap = mixed ? direct_cap_slots(lc, true) : 0;
         CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),
                       dim3(kWinThreads), 0, st, lc->view(), params, W, priors, lc->ws, lnprob, loglike, sc));
         g_launches++;
     }
     lc->timer.mark(1, st);
-    const int rc = launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
+    const int rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
+                         : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     lc->timer.mark(2, st);
     lc->timer.done();
     return rc;

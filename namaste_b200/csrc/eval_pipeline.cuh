@@ -57,6 +57,8 @@ struct EvalWs {
     int maxslots;        // slots per walker are capped; longer ranges put several passes in a slot
     int tsw;             // timestamps per slot: as many whole bins as fit in kEvalPass supersamples
     int merge;           // consecutive slots of a walker a warp evaluates in one pass (<= kEvalMerge)
+    int direct_cap;      // > 0: walkers with at most this many single-pass slots are not queued; a block of
+                         // eval_mixed_kernel evaluates each of them on the spot (0: every walker is queued)
     double* modelbuf;    // GP mode only (else null): [CW][npad] binned model of the in-transit timestamps;
                          // stage 2 stores it instead of reducing residuals and nobody finishes walkers
     unsigned long long* trace;  // diagnostics (NMB_TRACE): [16] phase envelopes in globaltimer ns, else null
@@ -106,7 +108,8 @@ __device__ __forceinline__ void push_slots(const EvalWs& ws, long long cw, int l
     constexpr int NWARP = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int pps;
-    const int mine = slots_for(hi - lo, ws.tsw, ws.maxslots, pps);
+    int mine = slots_for(hi - lo, ws.tsw, ws.maxslots, pps);
+    if (pps == 1 && mine <= ws.direct_cap) mine = 0;  // left to a direct block of eval_mixed_kernel
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -573,13 +576,12 @@ struct EvalSmem {
     WalkerConsts wc[THREADS / 32];
 };
 
-template <int S, int THREADS, int MINB, int PATH>
-__global__ void __launch_bounds__(THREADS, MINB)
-eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
-                  int nsm, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
+template <int S, int THREADS, int PATH>
+__device__ __forceinline__ void
+eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, const double* __restrict__ params, int W,
+                const double* __restrict__ priors, const EvalWs& ws, int nsm, double* __restrict__ lnprob,
+                double* __restrict__ loglike, const SampleCtx& sc) {
     constexpr int NWARP = THREADS / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    EvalSmem<THREADS>& sm = *reinterpret_cast<EvalSmem<THREADS>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Sx = s_of<S>(lc.S);
     const int SP = Sx | 1;
@@ -592,7 +594,7 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
     // warp index that runs over SMs first, then sub-partitions, then resident blocks of an SM
     // (blocks b, b + nsm, ... share an SM in a one-wave launch), so a short queue still touches
     // every sub-partition of the GPU
-    const int nwarps = gridDim.x * NWARP;
+    const int nwarps = nblocks * NWARP;
     const int gw = (((int)blockIdx.x / nsm) * NWARP + warp) * nsm + (int)blockIdx.x % nsm;
     // chunks of slots: the first chunk of a warp is its own index (no atomic on the way to the first
     // sample), further chunks come from a shared counter, fetched one chunk ahead.  Small queues are
@@ -772,12 +774,21 @@ eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const dou
     if (threadIdx.x == 0) {
         __threadfence();
         const int done = atomicAdd(ws.counters + 3, 1);
-        if (done == (int)gridDim.x - 1) {
+        if (done == nblocks - 1) {
             ws.counters[1] = 0;
             ws.counters[2] = 0;
             ws.counters[3] = 0;
         }
     }
+}
+
+template <int S, int THREADS, int MINB, int PATH>
+__global__ void __launch_bounds__(THREADS, MINB)
+eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
+                  int nsm, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    eval_slots_body<S, THREADS, PATH>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), (int)gridDim.x, lc, params, W, priors,
+                                      ws, nsm, lnprob, loglike, sc);
 }
 
 // ---- windowed mode, direct evaluation: one thread block per walker ------------------------------
@@ -799,6 +810,134 @@ struct DirectSmem {
     double part[(THREADS / 32) * kEvalMerge];
     int first;
 };
+
+// The direct evaluation proper, shared by window_direct_kernel (range and constants derived in the block)
+// and eval_mixed_kernel (range and constants left in the workspace by stage 1).  On entry sm.wc[warp]
+// holds the walker's constants; warp w takes the consecutive slots [w * per, (w + 1) * per) as one pass.
+// `ln_prior_w0()` / `oot_w0()` are evaluated by warp 0 only.
+template <int S, int THREADS, int PATH, class LnPrior, class Oot>
+__device__ __forceinline__ void
+direct_eval_tail(DirectSmem<THREADS>& sm, const LcView& lc, const EvalWs& ws, const SampleCtx& sc, int cw, int cand, int W,
+                 int ilo, int ihi, int nsl, double* __restrict__ lnprob, double* __restrict__ loglike, LnPrior ln_prior_w0,
+                 Oot oot_w0) {
+    constexpr int NWARP = THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Sx = s_of<S>(lc.S);
+    const int SP = Sx | 1;
+    const int TSW = ws.tsw;
+    WalkerConsts& wc = sm.wc[warp];
+    QuadConstsF cf = QuadConstsF{};
+    if (PATH == 2) cf = to_f32(wc.q);
+    const int per = (nsl + NWARP - 1) / NWARP;
+    const int s0 = warp * per, s1 = min(nsl, s0 + per);
+    if (s0 < s1) {
+        double* scratch = sm.scratch[warp];
+        double* terms = scratch + kEvalMerge * (2 * kEvalPass + 8);
+        const double* gt = lc.t + (long long)cand * lc.npad;
+        const double* gf = lc.f + (long long)cand * lc.npad;
+        const double* gw_ = lc.w + (long long)cand * lc.npad;
+        const double* goff = lc.off + (long long)cand * Sx;
+        const int t0 = ilo + s0 * TSW, tend = min(ihi, ilo + s1 * TSW);
+        const int nts = tend - t0;
+        const int nsamp = nts * Sx;
+        // flux and weight of the first 32 timestamps of the pass: requested before the flux rounds
+        const double f_pre = lane < nts ? __ldg(gf + t0 + lane) : 0.0;
+        const double w_pre = lane < nts ? __ldg(gw_ + t0 + lane) : 0.0;
+        for (int j = lane; j < nsamp; j += 32) {
+            const int h = j / Sx, k = j - h * Sx;
+            scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + t0 + h), __ldg(goff + k), wc, cf, &wc.q);
+            if (ws.trace && j == lane && lane == 0) trace_max(ws, 6);  // first flux round of a direct pass done
+        }
+        __syncwarp();
+        if (lane == 0) trace_max(ws, 14);  // flux rounds of a direct pass done
+        for (int h = lane; h < nts; h += 32) {
+            const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + h * SP) : bin_mean_rt(scratch + h * SP, Sx);
+            const double r = (h == lane ? f_pre : __ldg(gf + t0 + h)) - m;
+            terms[h] = (h == lane ? w_pre : __ldg(gw_ + t0 + h)) * (r * r);
+        }
+        __syncwarp();
+        for (int q = 0; q < s1 - s0; ++q) {
+            const int b0 = q * TSW, nq = min(TSW, nts - b0);
+            double acc = 0.0;
+            for (int h = lane; h < nq; h += 32) acc += terms[b0 + h];
+            acc = warp_sum(acc);
+            if (lane == 0) sm.part[s0 + q] = acc;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double ssum = 0.0;
+        for (int c = lane; c < nsl; c += 32) ssum += sm.part[c];
+        ssum = warp_sum(ssum);
+        if (lane == 0) trace_max(ws, 15);  // slot partials of a direct block folded
+        const double lp = ln_prior_w0();
+        if (lane == 0) {
+            finish_walker(sc, cw, W, oot_w0() + ssum, lp, lnprob, loglike);
+            trace_max(ws, 10);
+        }
+    }
+}
+
+// ---- stage 2 for ensembles of about one resident wave: queue workers and direct blocks in one launch ----
+// Blocks [0, nq) are eval_slots workers on the queue, which stage 1 filled only with walkers of more than
+// `direct_cap` slots (slow or grazing walkers).  Block nq + cw looks at walker cw: if stage 1 left it a short
+// in-transit range, the block evaluates it on the spot (one pass per warp, partials folded in shared memory)
+// with two dependent global round trips (range + constants, then the pass's light-curve lines) where the
+// queue needs eight.  The two kinds of block do not communicate; results have the same bits either way.
+template <int S, int THREADS, int MINB, int PATH>
+__global__ void __launch_bounds__(THREADS, MINB)
+eval_mixed_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
+                  int nsm, int nq, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
+    constexpr int NWARP = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if ((int)blockIdx.x < nq) {
+        eval_slots_body<S, THREADS, PATH>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), nq, lc, params, W, priors, ws, nsm,
+                                          lnprob, loglike, sc);
+        return;
+    }
+    DirectSmem<THREADS>& sm = *reinterpret_cast<DirectSmem<THREADS>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cw = (int)blockIdx.x - nq;
+    const int cand = cw / W;
+    // the finishing warp's row of the prior table does not depend on stage 1: load it first
+    double pr_lo = 0.0, pr_hi = 0.0, pr_kind = 0.0, pr_mu = 0.0, pr_sg = 1.0;
+    if (priors && warp == 0 && lane < 6) {
+        const double* row = priors + (long long)cand * 36 + lane * 6;
+        pr_lo = __ldg(row); pr_hi = __ldg(row + 1); pr_kind = __ldg(row + 2); pr_mu = __ldg(row + 3); pr_sg = __ldg(row + 4);
+    }
+    pdl_wait();  // stage 1 complete: ranges, constants and out-of-transit sums visible
+    if (tid == 0) { trace_min(ws, 12); trace_max(ws, 13); }  // first / last direct block started
+    const int ilo = __ldcg(ws.rlo + cw), ihi = __ldcg(ws.rhi + cw);
+    int pps;
+    const int nsl = slots_for(ihi - ilo, ws.tsw, ws.maxslots, pps);
+    if (nsl == 0 || pps > 1 || nsl > ws.direct_cap) return;  // finished by stage 1, or on the queue
+    {   // the walker's constants into this warp's shared-memory copy
+        const double* src = reinterpret_cast<const double*>(ws.wcs + cw);
+        double* dst = reinterpret_cast<double*>(&sm.wc[warp]);
+        for (int i = lane; i < (int)(sizeof(WalkerConsts) / 8); i += 32) dst[i] = __ldcg(src + i);
+    }
+    double oot = 0.0, x_lane = 0.0;
+    if (warp == 0) {
+        oot = __ldcg(ws.oot + cw);
+        if (lane < 6) x_lane = __ldcg((sc.enabled ? sc.q : params) + (long long)cw * 6 + lane);
+    }
+    __syncwarp();
+    if (lane == 0) trace_max(ws, 5);  // constants of a direct block in shared memory
+    auto ln_prior_w0 = [&]() {
+        if (!priors) return 0.0;
+        double wall = 0.0, bump = 0.0;
+        if (lane < 6) ln_prior_terms_v(x_lane, pr_lo, pr_hi, (int)pr_kind, pr_mu, pr_sg, wall, bump);
+        double lp = 0.0;
+        for (int n = 0; n < 6; ++n) lp = (lp - __shfl_sync(0xffffffffu, wall, n)) + __shfl_sync(0xffffffffu, bump, n);
+        return lp;
+    };
+    direct_eval_tail<S, THREADS, PATH>(sm, lc, ws, sc, cw, cand, W, ilo, ihi, nsl, lnprob, loglike, ln_prior_w0,
+                                       [&]() { return oot; });
+    if (tid == 0) {  // leave the workspace idle for the next evaluation (as the queue path does)
+        ws.rlo[cw] = INT_MAX;
+        ws.rhi[cw] = 0;
+    }
+}
 
 template <int S, int THREADS, int MINB, int PATH>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -863,7 +1002,7 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
         if (tid == 0) trace_max(ws, 3);
         return;
     }
-    if (pps > 1 || nsl > NWARP * ws.merge) {  // more than one pass per warp: onto the queue
+    if (pps > 1 || nsl > ws.direct_cap) {  // too long for one block: onto the queue
         if (tid == 0) {
             sm.first = atomicAdd(ws.counters + 1, nsl);
             ws.oot[cw] = oot_words.value();
@@ -884,56 +1023,10 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
     }
 
     // ---- direct: warp w takes the consecutive slots [w * per, (w + 1) * per) as one pass
-    WalkerConsts& wc = sm.wc[warp];
-    if (lane == 0) wc = wcr;
+    if (lane == 0) sm.wc[warp] = wcr;
     __syncwarp();
-    QuadConstsF cf = QuadConstsF{};
-    if (PATH == 2) cf = to_f32(wc.q);
-    const int per = (nsl + NWARP - 1) / NWARP;
-    const int s0 = warp * per, s1 = min(nsl, s0 + per);
-    if (s0 < s1) {
-        double* scratch = sm.scratch[warp];
-        double* terms = scratch + kEvalMerge * (2 * kEvalPass + 8);
-        const double* gt = lc.t + (long long)cand * lc.npad;
-        const double* gf = lc.f + (long long)cand * lc.npad;
-        const double* gw_ = lc.w + (long long)cand * lc.npad;
-        const double* goff = lc.off + (long long)cand * Sx;
-        const int t0 = ilo + s0 * TSW, tend = min(ihi, ilo + s1 * TSW);
-        const int nts = tend - t0;
-        const int nsamp = nts * Sx;
-        // flux and weight of the first 32 timestamps of the pass: requested before the flux rounds
-        const double f_pre = lane < nts ? __ldg(gf + t0 + lane) : 0.0;
-        const double w_pre = lane < nts ? __ldg(gw_ + t0 + lane) : 0.0;
-        for (int j = lane; j < nsamp; j += 32) {
-            const int h = j / Sx, k = j - h * Sx;
-            scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + t0 + h), __ldg(goff + k), wc, cf, &wc.q);
-        }
-        __syncwarp();
-        for (int h = lane; h < nts; h += 32) {
-            const double m = (S > 0) ? bin_mean<(S > 0 ? S : 1)>(scratch + h * SP) : bin_mean_rt(scratch + h * SP, Sx);
-            const double r = (h == lane ? f_pre : __ldg(gf + t0 + h)) - m;
-            terms[h] = (h == lane ? w_pre : __ldg(gw_ + t0 + h)) * (r * r);
-        }
-        __syncwarp();
-        for (int q = 0; q < s1 - s0; ++q) {
-            const int b0 = q * TSW, nq = min(TSW, nts - b0);
-            double acc = 0.0;
-            for (int h = lane; h < nq; h += 32) acc += terms[b0 + h];
-            acc = warp_sum(acc);
-            if (lane == 0) sm.part[s0 + q] = acc;
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        double ssum = 0.0;
-        for (int c = lane; c < nsl; c += 32) ssum += sm.part[c];
-        ssum = warp_sum(ssum);
-        const double lp = ln_prior_w0();
-        if (lane == 0) {
-            finish_walker(sc, cw, W, oot_words.value() + ssum, lp, lnprob, loglike);
-            trace_max(ws, 3);
-        }
-    }
+    direct_eval_tail<S, THREADS, PATH>(sm, lc, ws, sc, cw, cand, W, ilo, ihi, nsl, lnprob, loglike, ln_prior_w0,
+                                       [&]() { return oot_words.value(); });
 }
 
 __global__ void init_ranges_kernel(int* rlo, int* rhi, int* itemsdone, int n) {

@@ -30,10 +30,22 @@ _LC_CACHE_MAX = 8
 
 
 def _fingerprint(a):
-    """Cheap identity + content probe of an array (address, layout, strided sample)."""
-    flat = a.reshape(-1)
-    step = max(1, flat.size // 97)
-    return (a.__array_interface__["data"][0], a.shape, a.strides, float(flat[::step].sum()), float(flat[-1]))
+    """Identity + content key of an array: address and layout, plus two wrap-around checksums over EVERY
+    64-bit word of its float64 image, the plain sum and the sum weighted by the odd numbers (which makes
+    it sensitive to position); ~20 us for a 4000-point light curve.  A sampled probe is not enough: a
+    light curve re-detrended in place, or a new array that lands on a freed address with the same times
+    and errors, differs from the staged one only in some flux values."""
+    bits = np.ascontiguousarray(a, dtype=np.float64).reshape(-1).view(np.uint64)
+    odd = _ODD.get(bits.size)
+    if odd is None:
+        if len(_ODD) > 16:
+            _ODD.clear()
+        odd = _ODD[bits.size] = (np.arange(bits.size, dtype=np.uint64) << np.uint64(1)) | np.uint64(1)
+    return (a.__array_interface__["data"][0], a.shape, a.strides,
+            int(np.add.reduce(bits, dtype=np.uint64)), int(np.dot(bits, odd)))
+
+
+_ODD = {}
 
 
 def stage_lightcurve(lc, oversamp=10):
