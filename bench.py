@@ -307,6 +307,7 @@ def run_ours(args):
     staged.stage_timing(True)
     device_loop("brute", args.steps)
     ms_s1, ms_s2, _ = staged.stage_times()
+    k_s1, k_s2 = staged.last_kernels()   # stage 2 is eval_mixed_kernel or eval_slots_kernel, by ensemble size
     staged.stage_timing(False)
     device_loop("windowed", max(args.warmup, 3))
     ms_win, _, _ = device_loop("windowed", args.steps)
@@ -435,7 +436,7 @@ def run_ours(args):
         except Exception:
             traffic = {}
     kernels = []
-    for name, ms, fl in (("sweep_walkers_kernel", ms_s1, fl_sweep), ("eval_slots_kernel", ms_s2, fl_eval)):
+    for name, ms, fl in ((k_s1, ms_s1, fl_sweep), (k_s2, ms_s2, fl_eval)):
         tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         kernels.append({"kernel": name, "ms_per_launch": ms,
                         "share_of_step": ms / (ms_s1 + ms_s2) if ms_s1 + ms_s2 > 0 else None,

@@ -167,6 +167,9 @@ int nmb_measure_fp64_peak(double* tflops, double* ms);
  * enable, run evaluations, then read the mean stage-1 / stage-2 kernel durations in ms (and reset) */
 int nmb_stage_timing(nmb_lc* lc, int enable);
 int nmb_stage_times(nmb_lc* lc, double* stage1_ms, double* stage2_ms, int64_t* count);
+/* names of the stage-1 / stage-2 kernels the last nmb_lnprob evaluation on this handle launched (static
+ * strings): the pipeline picks them by mode and ensemble size, and bench.py reports what actually ran */
+int nmb_last_kernels(nmb_lc* lc, const char** stage1, const char** stage2);
 /* diagnostics: phase envelopes (globaltimer ns) of the last evaluation; needs NMB_TRACE=1 in the environment */
 int nmb_debug_trace(nmb_lc* lc, uint64_t* out16);
 /* number of kernels this library has launched so far in this process */

@@ -63,6 +63,7 @@ SIGNATURES = {
                                    ctypes.c_int, ctypes.c_double, _vp]),
     "nmb_measure_fp64_peak": (ctypes.c_int, [_c_double_p, _c_double_p]),
     "nmb_debug_trace": (ctypes.c_int, [_vp, _vp]),
+    "nmb_last_kernels": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p)]),
     "nmb_stage_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "nmb_stage_times": (ctypes.c_int, [_vp, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int64)]),
     "nmb_launch_count": (ctypes.c_int64, []),

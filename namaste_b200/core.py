@@ -130,6 +130,12 @@ class LightCurve:
                              ctypes.c_void_p(stream)), "lnprob_device")
         return out
 
+    def last_kernels(self):
+        """Names of the (stage-1, stage-2) kernels the last evaluation launched."""
+        a, b = ctypes.c_char_p(), ctypes.c_char_p()
+        check(load().nmb_last_kernels(self._h, ctypes.byref(a), ctypes.byref(b)), "last_kernels")
+        return a.value.decode(), b.value.decode()
+
     def stage_timing(self, enable=True):
         """Switch per-kernel device timing of the two pipeline stages on or off (resets the means)."""
         check(load().nmb_stage_timing(self._h, 1 if enable else 0), "stage_timing")

@@ -79,6 +79,8 @@ struct StageTimer {
 };
 
 struct nmb_lc {
+    const char* last_stage1 = "";  // kernels of the last nmb_lnprob evaluation (nmb_last_kernels)
+    const char* last_stage2 = "";
     int64_t ncand = 0, nmax = 0, npad = 0;
     int S = 0;
     int gran = 64, ngran = 0;
@@ -406,17 +408,18 @@ int launch_mixed_mb(nmb_lc* lc, const double* params, int W, const double* prior
                     cudaStream_t st, const nmb::SampleCtx& sc) {
     auto kern = nmb::eval_mixed_kernel<S, kEvalThreads, MINB, PATH>;
     const size_t smem = std::max(sizeof(nmb::EvalSmem<kEvalThreads>), sizeof(nmb::DirectSmem<kEvalThreads>));
-    static thread_local int sms = 0;
+    static thread_local int sms = 0, per_sm = 0;
     if (!sms) {
         if (int rc = set_smem(kern, smem)) return rc;
         int dev = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEvalThreads, smem));
+        per_sm = std::max(per_sm, 1);
     }
-    // queue workers: two blocks per SM (the queue only holds the long-range walkers; measured on BASELINE
-    // config 2: 57.7 us with one, 51.7 with two, 51.6 with three)
-    static const int nq_per_sm = std::getenv("NMB_MIXED_NQ") ? std::max(1, std::atoi(std::getenv("NMB_MIXED_NQ"))) : 2;
-    const int nq = sms * nq_per_sm;
+    // queue workers: one resident wave, like eval_slots_kernel (those that find the queue empty exit at once)
+    static const int nq_force = std::getenv("NMB_MIXED_NQ") ? std::max(1, std::atoi(std::getenv("NMB_MIXED_NQ"))) : 0;
+    const int nq = sms * (nq_force ? nq_force : per_sm);
     const size_t CW = (size_t)lc->ncand * W;
     CU(launch_pdl(kern, dim3((unsigned)(nq + CW)), dim3(kEvalThreads), smem, st, lc->view(), params, W, priors, lc->ws, sms,
                   nq, lnprob, loglike, sc));
@@ -508,6 +511,8 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     lc->timer.mark(1, st);
     rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
                : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
+    lc->last_stage1 = "sweep_walkers_kernel";
+    lc->last_stage2 = mixed ? "eval_mixed_kernel" : "eval_slots_kernel";
     lc->timer.mark(2, st);
     lc->timer.done();
     return rc;
@@ -582,6 +587,8 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     lc->timer.mark(1, st);
     const int rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
                          : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
+    lc->last_stage1 = direct ? "window_direct_kernel" : "window_ranges_kernel";
+    lc->last_stage2 = mixed ? "eval_mixed_kernel" : "eval_slots_kernel";
     lc->timer.mark(2, st);
     lc->timer.done();
     return rc;
@@ -845,6 +852,13 @@ extern "C" int nmb_debug_trace(nmb_lc* lc, uint64_t* out) {
     uint64_t init[16] = {0};
     init[0] = init[8] = ~0ull;
     CU(cudaMemcpy(lc->ws.trace, init, sizeof init, cudaMemcpyHostToDevice));
+    return NMB_OK;
+}
+
+extern "C" int nmb_last_kernels(nmb_lc* lc, const char** stage1, const char** stage2) {
+    if (!lc || !stage1 || !stage2) return fail(NMB_ERR_ARG, "nmb_last_kernels: null pointer");
+    *stage1 = lc->last_stage1;
+    *stage2 = lc->last_stage2;
     return NMB_OK;
 }
 

@@ -576,7 +576,7 @@ struct EvalSmem {
     WalkerConsts wc[THREADS / 32];
 };
 
-template <int S, int THREADS, int PATH>
+template <int S, int THREADS, int PATH, bool PACKED>
 __device__ __forceinline__ void
 eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, const double* __restrict__ params, int W,
                 const double* __restrict__ priors, const EvalWs& ws, int nsm, double* __restrict__ lnprob,
@@ -595,7 +595,10 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, cons
     // (blocks b, b + nsm, ... share an SM in a one-wave launch), so a short queue still touches
     // every sub-partition of the GPU
     const int nwarps = nblocks * NWARP;
-    const int gw = (((int)blockIdx.x / nsm) * NWARP + warp) * nsm + (int)blockIdx.x % nsm;
+    // (PACKED, eval_mixed_kernel: block after block instead, so that a short queue keeps few blocks busy and
+    // the others leave their SM slots to the direct blocks at once)
+    const int gw = PACKED ? (int)blockIdx.x * NWARP + warp
+                          : (((int)blockIdx.x / nsm) * NWARP + warp) * nsm + (int)blockIdx.x % nsm;
     // chunks of slots: the first chunk of a warp is its own index (no atomic on the way to the first
     // sample), further chunks come from a shared counter, fetched one chunk ahead.  Small queues are
     // dealt out in one chunk per warp; large ones in chunks of at least one merged pass.
@@ -787,8 +790,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
 eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
                   int nsm, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    eval_slots_body<S, THREADS, PATH>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), (int)gridDim.x, lc, params, W, priors,
-                                      ws, nsm, lnprob, loglike, sc);
+    eval_slots_body<S, THREADS, PATH, false>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), (int)gridDim.x, lc, params, W,
+                                             priors, ws, nsm, lnprob, loglike, sc);
 }
 
 // ---- windowed mode, direct evaluation: one thread block per walker ------------------------------
@@ -879,11 +882,14 @@ direct_eval_tail(DirectSmem<THREADS>& sm, const LcView& lc, const EvalWs& ws, co
 }
 
 // ---- stage 2 for ensembles of about one resident wave: queue workers and direct blocks in one launch ----
-// Blocks [0, nq) are eval_slots workers on the queue, which stage 1 filled only with walkers of more than
-// `direct_cap` slots (slow or grazing walkers).  Block nq + cw looks at walker cw: if stage 1 left it a short
-// in-transit range, the block evaluates it on the spot (one pass per warp, partials folded in shared memory)
-// with two dependent global round trips (range + constants, then the pass's light-curve lines) where the
-// queue needs eight.  The two kinds of block do not communicate; results have the same bits either way.
+// Blocks [0, nq) (one resident wave, dispatched first) are eval_slots workers on the queue, which stage 1
+// filled only with walkers of more than `direct_cap` slots (slow or grazing walkers; every walker of a long
+// light curve).  The queue is dealt to them block after block, so with a short queue most of them find
+// nothing and exit at once.  Block nq + cw then takes a free SM slot and looks at walker cw: if stage 1 left
+// it a short in-transit range, the block evaluates it on the spot (one pass per warp, partials folded in
+// shared memory) with two dependent global round trips (range + constants, then the pass's light-curve
+// lines) where the queue needs eight; if the walker was queued or finished, the block exits.  The two kinds
+// of block do not communicate; results have the same bits either way.
 template <int S, int THREADS, int MINB, int PATH>
 __global__ void __launch_bounds__(THREADS, MINB)
 eval_mixed_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
@@ -891,8 +897,8 @@ eval_mixed_kernel(LcView lc, const double* __restrict__ params, int W, const dou
     constexpr int NWARP = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x < nq) {
-        eval_slots_body<S, THREADS, PATH>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), nq, lc, params, W, priors, ws, nsm,
-                                          lnprob, loglike, sc);
+        eval_slots_body<S, THREADS, PATH, true>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), nq, lc, params, W, priors, ws,
+                                                nsm, lnprob, loglike, sc);
         return;
     }
     DirectSmem<THREADS>& sm = *reinterpret_cast<DirectSmem<THREADS>*>(smem_raw);

@@ -9,7 +9,7 @@ done
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>&1
 python bench.py --steps 5 --warmup 3 --profile > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --profile > gpurun_out/ncu1.log 2>&1
-for k in sweep_walkers eval_slots window_ranges window_direct; do
+for k in sweep_walkers eval_mixed eval_slots window_ranges window_direct; do
 python bench.py --steps 5 --warmup 3 --profile > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -o gpurun_out/prof_$k -f python bench.py --steps 5 --warmup 3 --profile > gpurun_out/ncu_$k.log 2>&1
 done

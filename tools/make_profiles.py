@@ -22,7 +22,7 @@ def traffic(rep):
 
 
 tr = {"k2": {}, "kepler": {}}
-for k in ("sweep_walkers", "eval_slots", "window_ranges", "window_direct", "sweep_walkers_kepler"):
+for k in ("sweep_walkers", "eval_mixed", "eval_slots", "window_ranges", "window_direct", "sweep_walkers_kepler"):
     rep = os.path.join(go, "prof_%s.ncu-rep" % k)
     if os.path.exists(rep + ".gz"):
         subprocess.run(["gunzip", "-f", rep + ".gz"], check=True)
