@@ -110,3 +110,55 @@ def test_full_size_properties(nb, name, nspot):
         ref = o.mono_only_logprob(pos[i], wl["lc"], pri, wl["S"])
         assert abs(brute[i] - ref) <= 1e-10 * abs(ref) and abs(win[i] - ref) <= 1e-10 * abs(ref), i
     staged.close()
+
+
+_PATH_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import namaste_b200 as nb
+from conftest import load_golden
+g = load_golden("synth_k2_s11")
+rng = np.random.default_rng(12)
+base = g["walkers"][0]
+out = {}
+for W in (40, 320, 1000):
+    pos = base[None, :] * (1 + 1e-3 * rng.standard_normal((W, 6)))
+    pos[: W // 16, 2] *= rng.uniform(0.03, 0.6, W // 16)      # slow walkers: long ranges, always queued
+    pos[W // 16: W // 8, 1] = rng.uniform(1.0, 1.3, W // 8 - W // 16)   # grazing or never in transit
+    lc = nb.LightCurve(g["lc"], oversamp=int(g["oversamp"]))
+    for mode in ("brute", "windowed"):
+        for dt in ("f64", "strict"):
+            out["%d_%s_%s" % (W, mode, dt)] = lc.lnprob(pos, g["priors"], mode=mode, dtype=dt)
+            s1, s2 = lc.last_kernels()
+            out["k_%d_%s" % (W, mode)] = np.array([s1 + "+" + s2])
+    lc.close()
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_direct_and_mixed_stage2_give_the_queue_paths_bits(tmp_path):
+    """window_direct_kernel / eval_mixed_kernel (block per walker) against the pure queue pipeline
+    (NMB_DIRECT=0, NMB_MIXED_MAXCW=0 in a second process): identical bits for every walker, mode and
+    arithmetic, on ensembles that take each of the paths."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "paths.py"
+    script.write_text(_PATH_SCRIPT)
+    res = {}
+    for tag, env in (("default", {}), ("queue", {"NMB_DIRECT": "0", "NMB_MIXED_MAXCW": "0"})):
+        out = tmp_path / (tag + ".npz")
+        subprocess.run([sys.executable, str(script), root, str(out)], check=True, env={**os.environ, **env})
+        res[tag] = np.load(out)
+    d, q = res["default"], res["queue"]
+    assert str(d["k_40_windowed"][0]) == "window_direct_kernel+eval_slots_kernel"
+    assert str(d["k_320_windowed"][0]) == "window_direct_kernel+eval_slots_kernel"
+    assert str(d["k_1000_windowed"][0]) == "window_ranges_kernel+eval_mixed_kernel"
+    assert str(d["k_320_brute"][0]) == "sweep_walkers_kernel+eval_mixed_kernel"
+    assert str(d["k_40_brute"][0]) == "sweep_walkers_kernel+eval_slots_kernel"
+    for k in ("k_40_windowed", "k_320_windowed", "k_1000_windowed", "k_320_brute"):
+        assert str(q[k][0]).endswith("eval_slots_kernel") and "direct" not in str(q[k][0])
+    for key in d.files:
+        if key.startswith("k_"):
+            continue
+        assert np.array_equal(d[key], q[key], equal_nan=True), key
+        assert np.isfinite(d[key]).all()
