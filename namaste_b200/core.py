@@ -103,7 +103,10 @@ class LightCurve:
         W = p.shape[1]
         tab = prior_table(priors)
         if tab is not None:
-            tab = np.ascontiguousarray(np.broadcast_to(tab, (self.ncand, 6, 6)))
+            if tab.size == self.ncand * 36:          # already one table per candidate: no copy
+                tab = tab.reshape(self.ncand, 6, 6)
+            else:
+                tab = np.ascontiguousarray(np.broadcast_to(tab, (self.ncand, 6, 6)))
         out = np.empty((self.ncand, W))
         ll = np.empty((self.ncand, W)) if return_loglike else None
         check(lib.nmb_lnprob_host(self._h, ptr(p), W, ptr(tab), ptr(out), ptr(ll), MODES[mode], DTYPES[dtype]), "lnprob")

@@ -376,8 +376,7 @@ __device__ __forceinline__ int bsearch_t(const double* __restrict__ t, int n, do
 // early and pay their latency under other work.
 struct window_oot {
     double hn, hh, hl, ln, lh, ll;
-    __device__ __forceinline__ window_oot(const LcView& lc, int cand, int ilo, int ihi) {
-        const int n = (int)lc.n[cand];
+    __device__ __forceinline__ window_oot(const LcView& lc, int cand, int n, int ilo, int ihi) {
         const double* ph = lc.pre_hi + (long long)cand * (lc.npad + 1);
         const double* pl = lc.pre_lo + (long long)cand * (lc.npad + 1);
         hn = ph[n]; hh = ph[ihi]; hl = ph[ilo];
@@ -396,10 +395,25 @@ struct window_oot {
 // Conservative in-transit index range [ilo, ihi) of one walker from the geometry (O(1): two lookups in
 // the uniform time grid) and the chi^2 of everything outside it from the double-double prefix sums.
 // Exact: the range is a superset of the in-transit timestamps and stage 2 classifies every sample.
-__device__ __forceinline__ void walker_range(const LcView& lc, int cand, const WalkerConsts& wc, int Sx, int& ilo,
-                                             int& ihi) {
-    const int n = (int)lc.n[cand];
-    const double span = lc.off[(long long)cand * Sx + Sx - 1];
+// Per-candidate scalars of the window lookup.  They belong to the staged light curve, so a kernel loads them
+// before its grid dependency resolves and before the walker's own chain of dependent loads starts.
+struct CandGeom {
+    int n, gc;
+    double span, t0, ginv;
+};
+__device__ __forceinline__ CandGeom load_cand_geom(const LcView& lc, int cand, int Sx) {
+    CandGeom g;
+    g.n = (int)lc.n[cand];
+    g.gc = lc.gcount[cand];
+    g.span = lc.off[(long long)cand * Sx + Sx - 1];
+    g.t0 = lc.t0[cand];
+    g.ginv = lc.ginv[cand];
+    return g;
+}
+__device__ __forceinline__ void walker_range(const LcView& lc, int cand, const WalkerConsts& wc, const CandGeom& geo,
+                                             int& ilo, int& ihi) {
+    const int n = geo.n;
+    const double span = geo.span;
     const double hx2 = wc.qthr - wc.b2;
     bool full = !(wc.fbar == 1.0);  // prefix sums assume the out-of-transit model is exactly 1
     bool empty = false;
@@ -423,8 +437,8 @@ __device__ __forceinline__ void walker_range(const LcView& lc, int cand, const W
         ilo = 0; ihi = 0;
     } else {
         // O(1) lookup in the uniform time grid, widened by one cell on each side
-        const double t0 = lc.t0[cand], ginv = lc.ginv[cand];
-        const int gc = lc.gcount[cand];
+        const double t0 = geo.t0, ginv = geo.ginv;
+        const int gc = geo.gc;
         const int* __restrict__ grid = lc.tgrid + (long long)cand * lc.gstride;
         const double jl = floor((tlo - t0) * ginv) - 1.0, jh = floor((thi - t0) * ginv) + 2.0;
         const int j0 = jl < 0.0 ? 0 : (jl > (double)gc ? gc : (int)jl);
@@ -434,10 +448,10 @@ __device__ __forceinline__ void walker_range(const LcView& lc, int cand, const W
         if (ihi < ilo) ihi = ilo;
     }
 }
-__device__ __forceinline__ void walker_window(const LcView& lc, int cand, const WalkerConsts& wc, int Sx, int& ilo,
-                                              int& ihi, double& oot) {
-    walker_range(lc, cand, wc, Sx, ilo, ihi);
-    oot = window_oot(lc, cand, ilo, ihi).value();
+__device__ __forceinline__ void walker_window(const LcView& lc, int cand, const WalkerConsts& wc, const CandGeom& geo,
+                                              int& ilo, int& ihi, double& oot) {
+    walker_range(lc, cand, wc, geo, ilo, ihi);
+    oot = window_oot(lc, cand, geo.n, ilo, ihi).value();
 }
 
 template <int THREADS>
@@ -450,6 +464,8 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
     int lo_w = 0, hi_w = 0;
     const int cw = blockIdx.x * THREADS + tid;
     const int Sx = lc.S;
+    CandGeom geo = CandGeom{};
+    if (cw < CW) geo = load_cand_geom(lc, cw / W, Sx);
     pdl_wait();     // walker positions come from the previous kernel
     pdl_trigger();  // stage 2 may be scheduled; it waits for this grid to finish before reading
     if (tid == 0) trace_min(ws, 0);
@@ -463,7 +479,7 @@ window_ranges_kernel(LcView lc, const double* __restrict__ params, int W, const 
         const WalkerConsts wc = make_walker_consts(par + (long long)cw * 6, Sx);
         int ilo, ihi;
         double oot;
-        walker_window(lc, cand, wc, Sx, ilo, ihi, oot);
+        walker_window(lc, cand, wc, geo, ilo, ihi, oot);
         if (ihi - ilo <= 0) {  // never in transit: done here (the GP solve reads the idle range instead)
             if (!ws.modelbuf) {
                 const double lp = priors ? ln_prior_dev(par + (long long)cw * 6, priors + (long long)cand * 36, 6) : 0.0;
@@ -964,6 +980,7 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
         const double* row = priors + (long long)cand * 36 + lane * 6;
         pr_lo = __ldg(row); pr_hi = __ldg(row + 1); pr_kind = __ldg(row + 2); pr_mu = __ldg(row + 3); pr_sg = __ldg(row + 4);
     }
+    const CandGeom geo = load_cand_geom(lc, cand, Sx);
     pdl_wait();     // walker positions come from the previous kernel
     pdl_trigger();  // eval_slots_kernel may be scheduled; it waits for this grid to finish before reading
     if (tid == 0) trace_min(ws, 0);
@@ -984,11 +1001,11 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
         if (lane == d) x_lane = p6[d];
     const WalkerConsts wcr = make_walker_consts(p6, Sx);
     int ilo, ihi;
-    walker_range(lc, cand, wcr, Sx, ilo, ihi);
+    walker_range(lc, cand, wcr, geo, ilo, ihi);
     int pps;
     const int nsl = slots_for(ihi - ilo, TSW, ws.maxslots, pps);
     // out-of-transit chi^2: the loads go out now, the finishing warp combines them after its pass
-    const window_oot oot_words(lc, cand, warp == 0 ? ilo : 0, warp == 0 ? ihi : 0);
+    const window_oot oot_words(lc, cand, geo.n, warp == 0 ? ilo : 0, warp == 0 ? ihi : 0);
 
     // priors of the walker, one parameter per lane of warp 0, summed in the reference's order
     auto ln_prior_w0 = [&]() {
