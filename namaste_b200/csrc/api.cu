@@ -390,16 +390,11 @@ template <int S>
 int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     if (dtype == NMB_F32) return launch_eval_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
-    static const int minb = std::getenv("NMB_EVAL_MINB") ? std::atoi(std::getenv("NMB_EVAL_MINB")) : 0;
-    if (dtype != NMB_F64_STRICT) {
-        // five blocks (20 warps) per SM: the relaxed path fits 96 registers with two spilled words, and the
-        // shorter per-warp share of the queue outweighs them (measured: -4 % ... -7 % on every workload)
-        if (minb == 4) return launch_eval_mb<S, 4, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
-        return launch_eval_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
-    }
-    if (minb == 5) return launch_eval_mb<S, 5, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
-    if (minb == 6) return launch_eval_mb<S, 6, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
-    return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (dtype == NMB_F64_STRICT) return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
+    // relaxed path: five blocks (20 warps) per SM.  It fits 96 registers with two spilled words, and the shorter
+    // per-warp share of the queue outweighs them (measured: -4 % ... -7 % on every workload against four
+    // blocks; six blocks spill inside the flux rounds and lose)
+    return launch_eval_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
 
 // Stage 2 as one launch of queue workers + one direct block per walker (eval_mixed_kernel).
@@ -502,11 +497,8 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     static const int force_thr = std::getenv("NMB_SWEEP_THREADS") ? std::atoi(std::getenv("NMB_SWEEP_THREADS")) : 0;
     const long long blocks128 = (long long)lc->ncand * ((W + 127) / 128) * lc->ngran;
     const bool wide = force_thr ? (force_thr == 128) : (W >= 128 || blocks128 >= 4 * 148);
-    static const int minb = std::getenv("NMB_SWEEP_MINB") ? std::atoi(std::getenv("NMB_SWEEP_MINB")) : 8;
-    int rc = !wide       ? launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc)
-             : minb == 6 ? launch_sweep_t<S, 128, 6>(lc, params, W, priors, lnprob, loglike, st, sc)
-             : minb == 4 ? launch_sweep_t<S, 128, 4>(lc, params, W, priors, lnprob, loglike, st, sc)
-                         : launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc);
+    int rc = !wide ? launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc)
+                   : launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (rc) return rc;
     lc->timer.mark(1, st);
     rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
