@@ -16,8 +16,14 @@
 //   eval_slots_kernel     (both)             : resident warps share the queue of slots (passes of
 //       one walker's range); one supersample per lane and round, bins reduced in NumPy's order,
 //       slot partials stored and folded in slot order by the warp that completes a walker.
+//   eval_mixed_kernel     (both, mid-sized ensembles): the same queue workers plus one block per walker
+//       that evaluates a short range on the spot from what stage 1 left in the workspace; stage 1 then
+//       queues only the long ranges.
+//   window_direct_kernel  (NMB_MODE_WINDOWED, ensembles of one resident wave): one block per walker does
+//       proposal, constants, window, flux rounds, fold, priors and accept without leaving the SM.
 // Stage 1 pushes its walkers' slots with one atomicAdd per block; kernels are chained with
-// programmatic dependent launch so the next one is resident when its predecessor drains.
+// programmatic dependent launch so the next one is resident when its predecessor drains.  Whatever the
+// path, slot boundaries and summation trees are the same, so a walker's lnprob has the same bits.
 //
 // Why a range is enough: along the sorted supersample sequence fl(t_i + off_k) - tcen is monotone,
 // so fma(vx, vx, b^2) is V-shaped and {q <= threshold} is contiguous.
