@@ -23,7 +23,7 @@ from . import core
 
 __all__ = ["MonotransitModel", "MonoLnPrior", "MonoOnlyLogProb", "MonoOnlyNegLogProb", "CalcTdur", "CalcVel",
            "stage_lightcurve", "clear_cache", "calcminp", "calcmaxvel", "monoPriors", "initLD", "BuildMeanPriors",
-           "transit_window_mask", "initial_walkers", "trim_samples", "Optimize_mono", "VelToOrbit", "PlanetRtoM", "MonoFinalPars"]
+           "transit_window_mask", "nonan", "AnomCutDiff", "initial_walkers", "trim_samples", "Optimize_mono", "VelToOrbit", "PlanetRtoM", "MonoFinalPars"]
 
 _LC_CACHE = OrderedDict()
 _LC_CACHE_MAX = 8
@@ -235,6 +235,26 @@ def BuildMeanPriors(lc, tcen, tdur, sdenss, LD1s, LD2s, name="mean"):
     for key, row in initLD(LD1s, LD2s).items():
         priors[name + ":" + key] = row
     return priors
+
+
+def nonan(lc):
+    """Rows of a light curve that hold no NaN in any column (namaste.py:1456-1457)."""
+    return ~np.isnan(np.sum(np.asarray(lc, dtype=np.float64), axis=1))
+
+
+def AnomCutDiff(flux, thresh=4.2):
+    """Mask of the points to KEEP after the single-point outlier cut (namaste.py:1459-1467; Namaste calls
+    it with 3.75 before detrending, :64 / :1109).  An interior point is dropped only when it is a spike:
+    it differs from BOTH neighbours by at least ``thresh`` times the median absolute point-to-point
+    difference and the two steps have opposite signs.  Two outliers in a row, ramps and the end points
+    stay.  ``flux`` must be NaN-free (``nonan``).  Host NumPy like the reference: once per star."""
+    f = np.asarray(flux, dtype=np.float64)
+    step = np.diff(f)
+    # the reference scales by the median of |diff(flux[1:])|, i.e. without the first step
+    scale = np.median(np.abs(step[1:]))
+    ahead, behind = step[1:] / scale, step[:-1] / scale      # f[i+1] - f[i] and f[i] - f[i-1] for i = 1 .. n-2
+    keep = (ahead * behind > 0) | (np.abs(ahead) < thresh) | (np.abs(behind) < thresh)
+    return np.concatenate(([True], keep, [True]))
 
 
 def transit_window_mask(t, tcen, vel, b, RpRs, ndurswindow=6, two_sided=False):

@@ -40,3 +40,21 @@ def crossfield():
 def k2flatten():
     """namaste/k2flatten.py, unmodified."""
     return _load("_ref_k2flatten", "namaste/k2flatten.py")
+
+
+def namaste_function(name):
+    """One top-level function of namaste/namaste.py, compiled from the reference's own source text.
+
+    The module itself cannot be imported here (autograd, celerite, emcee, astropy are absent), but its
+    pure-NumPy helpers can be run as they are: the function definition is cut out of the file with
+    ``ast`` and executed in a namespace that only holds ``numpy as np``.  Build container only."""
+    import ast
+    import numpy as np
+    path = os.path.join(REFERENCE_ROOT, "namaste", "namaste.py")
+    src = open(path).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            ns = {"np": np}
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+            return ns[name]
+    raise KeyError(name)
