@@ -8,7 +8,7 @@ CUDA library (namaste_b200/csrc, C ABI in include/namaste_b200.h); there is no C
 """
 from .namaste import (MonotransitModel, MonoLnPrior, MonoOnlyLogProb, MonoOnlyNegLogProb, CalcTdur, CalcVel,
                       stage_lightcurve, clear_cache, calcminp, calcmaxvel, monoPriors, initLD, BuildMeanPriors,
-                      transit_window_mask, nonan, AnomCutDiff, initial_walkers, trim_samples, Optimize_mono, VelToOrbit, PlanetRtoM, MonoFinalPars)
+                      transit_window_mask, nonan, AnomCutDiff, initial_walkers, trim_samples, RunMCMC, Optimize_mono, VelToOrbit, PlanetRtoM, MonoFinalPars)
 from .sampler import EnsembleSampler
 from .gp import GP, RealTerm, JitterTerm, RotationTerm, MonoLogProb, MonoNegLogProb
 from .core import LightCurve, occultquad, lnprior, prior_table, measure_fp64_peak, launch_count, PARAM_NAMES

@@ -23,7 +23,7 @@ from . import core
 
 __all__ = ["MonotransitModel", "MonoLnPrior", "MonoOnlyLogProb", "MonoOnlyNegLogProb", "CalcTdur", "CalcVel",
            "stage_lightcurve", "clear_cache", "calcminp", "calcmaxvel", "monoPriors", "initLD", "BuildMeanPriors",
-           "transit_window_mask", "nonan", "AnomCutDiff", "initial_walkers", "trim_samples", "Optimize_mono", "VelToOrbit", "PlanetRtoM", "MonoFinalPars"]
+           "transit_window_mask", "nonan", "AnomCutDiff", "initial_walkers", "trim_samples", "RunMCMC", "Optimize_mono", "VelToOrbit", "PlanetRtoM", "MonoFinalPars"]
 
 _LC_CACHE = OrderedDict()
 _LC_CACHE_MAX = 8
@@ -296,6 +296,42 @@ def trim_samples(chain, lnprobability, nsteps):
     samples = chain[good_wlkrs, ncut:, :].reshape((-1, ndim))
     samples = np.column_stack((samples, lnprobability[good_wlkrs, ncut:].reshape(-1)))
     return samples, good_wlkrs, ncut
+
+
+# ---- the sampling run of one star (Star.RunMCMC, namaste.py:537-608, no-GP branch) -------------------
+def RunMCMC(lc, priors, pdfs, meanmodel, nwalkers=24, nsteps=12500, ndurswindow=6, rng=None, seed=None,
+            mode="windowed", two_sided_window=False):
+    """What ``Star.RunMCMC`` does between building the priors and saving the samples, for the transit-only
+    objective (``Settings.GP = False``), with the reference's defaults (24 walkers, 12 500 steps, window of
+    6 durations; namaste.py:57-61):
+
+    1. ``nwalkers`` distinct rows of the PDF table ``pdfs`` [npdf, 6] become the initial ensemble, NaNs
+       replaced as the reference replaces them (:537-547, ``initial_walkers``);
+    2. the light curve is cut to the window around ``meanmodel``'s transit (:550-556, including the
+       reference's one-sided quirk unless ``two_sided_window``);
+    3. ``EnsembleSampler(nwalkers, 6, MonoOnlyLogProb, args=(lc[mask], priors, meanmodel))`` runs one step
+       and then ``nsteps`` steps, both from the initial ensemble, the second call appending to the chain
+       (:590-594) -- proposal, likelihood and accept/reject stay on the GPU for the whole run;
+    4. burn-in cut ``min(nsteps/4, 3000)`` and failed-walker filter (:597-608, ``trim_samples``).
+
+    Returns a dict with ``samples`` [n, 7] (six parameters + ``logprob``), ``sampleheaders``, the
+    ``sampler`` (chain and lnprobability stay in HBM until read), ``mask``, ``init_mcmc_params``,
+    ``good_wlkrs`` and ``ncut``.  Plotting, logging and file output of the reference are not part of it."""
+    from .sampler import EnsembleSampler
+    lc = np.asarray(lc, dtype=np.float64)
+    init = initial_walkers(pdfs, nwalkers, rng=rng)
+    par = meanmodel.get_parameter_dict()
+    mask = transit_window_mask(lc[:, 0], par["tcen"], par["vel"], par["b"], par["RpRs"], ndurswindow,
+                               two_sided=two_sided_window)
+    fit_lc = np.ascontiguousarray(lc[mask, :])
+    sampler = EnsembleSampler(nwalkers, init.shape[1], MonoOnlyLogProb, args=(fit_lc, priors, meanmodel),
+                              mode=mode, seed=seed)
+    sampler.run_mcmc(init, 1)
+    sampler.run_mcmc(init, nsteps)
+    samples, good, ncut = trim_samples(sampler.chain, sampler.lnprobability, nsteps)
+    headers = ["mean:" + nm for nm in MonotransitModel.parameter_names] + ["logprob"]
+    return {"samples": samples, "sampleheaders": headers, "sampler": sampler, "mask": mask,
+            "init_mcmc_params": init, "good_wlkrs": good, "ncut": ncut}
 
 
 # ---- multi-start optimisation of the transit parameters (namaste.py:1010-1057) -----------------

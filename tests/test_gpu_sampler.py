@@ -100,3 +100,33 @@ def test_posterior_agrees_with_cpu_chain_statistically(nb):
         sd = 0.5 * (gpu[:, d].std() + cpu[:, d].std())
         # ~ (32 walkers * 300 steps) / tau(~60) independent samples per chain -> s.e. ~ sd / 12
         assert abs(np.median(gpu[:, d]) - np.median(cpu[:, d])) < 0.5 * sd, d
+
+
+def test_runmcmc_driver(nb):
+    """RunMCMC (Star.RunMCMC, namaste.py:537-608, transit-only branch) end to end on the example star:
+    initial ensemble from the reference's own PDF table, one-sided window quirk (N = 2828), 1 + nsteps
+    appended chain, trimming; the posterior sits on the reference's logged best fit."""
+    g = load_golden("priors_epic203311200")
+    c1 = load_golden("config1_epic203311200")
+    kat = load_golden("kat_epic203311200")
+    pri = priors_from_table(c1["priors"])
+    model = nb.MonotransitModel(*kat["params"][0])
+    # the flattened light curve RunMCMC sees = config 1's before the window cut; here its windowed form
+    # is used as the input, which the window mask keeps entirely (every t - tcen < 6 Tdur)
+    nsteps = 400
+    out = nb.RunMCMC(c1["lc"], pri, g["pdfs"], model, nwalkers=24, nsteps=nsteps,
+                     rng=np.random.default_rng(203311200), seed=7)
+    assert out["mask"].all() and out["mask"].shape == (2828,)
+    s = out["sampler"]
+    assert s.chain.shape == (24, 1 + nsteps, 6) and s.lnprobability.shape == (24, 1 + nsteps)
+    assert out["ncut"] == 100 and out["sampleheaders"][-1] == "logprob" and len(out["sampleheaders"]) == 7
+    smp = out["samples"]
+    assert smp.shape == (int(out["good_wlkrs"].sum()) * (1 + nsteps - 100), 7) and np.isfinite(smp).all()
+    assert out["good_wlkrs"].sum() >= 12
+    # rows of the PDF table, NaN -> 0.0 as the reference does
+    assert out["init_mcmc_params"].shape == (24, 6) and np.isfinite(out["init_mcmc_params"]).all()
+    best = kat["params"][0]
+    med = np.median(smp[:, :6], axis=0)
+    assert abs(med[0] - best[0]) < 0.01            # tcen [d]
+    assert abs(med[3] - best[3]) < 0.01            # RpRs
+    assert np.median(smp[:, 6]) >= np.median(s.lnprobability[:, 0])   # the ensemble moved uphill from the PDF draws
