@@ -898,7 +898,7 @@ direct_eval_tail(DirectSmem<THREADS>& sm, const LcView& lc, const EvalWs& ws, co
         const double lp = ln_prior_w0();
         if (lane == 0) {
             finish_walker(sc, cw, W, oot_w0() + ssum, lp, lnprob, loglike);
-            trace_max(ws, 10);
+            trace_max(ws, 7);  // walker of a direct block finished
         }
     }
 }

@@ -41,8 +41,8 @@ def run(lib, z, p, g1, g2, path):
 def sample_z(rng, p, n):
     """Uniform over the disc plus points crowding the three singular radii z = p, 1 - p, 1 + p."""
     near = lambda c, sgn: c + sgn * 10.0 ** rng.uniform(-14, -2, n // 10)
-    return np.concatenate([rng.uniform(0, 1 + p + 0.05, n), near(p, +1), near(1 - p, +1), near(1 - p, -1),
-                           near(1 + p, -1)])
+    return np.concatenate([rng.uniform(0, 1 + p + 0.05, n), near(p, +1), near(p, -1), near(0.0, +1), near(1 - p, +1),
+                           near(1 - p, -1), near(1 + p, -1)])
 
 
 @pytest.mark.parametrize("path,bound", [(1, 5e-14), (3, 1e-13)])
@@ -57,9 +57,10 @@ def test_hot_paths_match_oracle(hostmath, path, bound):
         z = sample_z(rng, p, 20000)
         ref = o.occultquad(z, p, [g1, g2])
         F, ok = run(hostmath, z, p, g1, g2, path)
-        inside = (z > p) & (z < 1 + p) & (z != 1 - p)
+        inside = (z > 0) & (z != p) & (z < 1 + p) & (z != 1 - p)
         assert ok[inside].mean() > 0.999          # the hot path takes (almost) every in-transit sample
-        assert not ok[z > 1 + p].any() and not ok[z < p].any()
+        assert not ok[z > 1 + p].any()
+        assert ok[(z > 0) & (z < p)].all()        # planet over the disc centre (case i09): Lambda_2 as well
         worst = max(worst, float(np.abs(F[ok] - ref[ok]).max()))
         covered += int(ok.sum())
     print("path", path, "elements", covered, "worst |dF|", worst)

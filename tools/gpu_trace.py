@@ -22,7 +22,7 @@ out = torch.empty((1, len(pos)), dtype=torch.float64, device="cuda")
 flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 lib = load()
 buf = np.zeros(16, dtype=np.uint64)
-names = {5: "direct consts in smem", 6: "direct first round done", 1: "s1 consts ready", 2: "s1 sweep/window done", 3: "s1 fold done", 4: "s1 scan done", 8: "s2 first block start",
+names = {7: "direct walker finished", 5: "direct consts in smem", 6: "direct first round done", 1: "s1 consts ready", 2: "s1 sweep/window done", 3: "s1 fold done", 4: "s1 scan done", 8: "s2 first block start",
          9: "s2 first items known", 10: "s2 last item evaluated", 11: "s2 last warp done",
          12: "direct first start", 13: "direct last start", 14: "direct rounds done", 15: "direct folded"}
 for rep in range(6):
