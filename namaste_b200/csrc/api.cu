@@ -432,8 +432,12 @@ int launch_mixed(nmb_lc* lc, const double* params, int W, const double* priors, 
 
 // Ensembles between a few hundred walkers and about two resident waves of direct blocks take the mixed
 // stage 2: short ranges are evaluated by a block per walker, only long ranges are queued.  Below that the
-// queue alone already gives every slot its own warp (config 1, 100 walkers: 30.6 us against 31.9 us mixed);
-// above it the queue balances better than waves of blocks.  NMB_MIXED_MINCW / NMB_MIXED_MAXCW override.
+// queue alone already gives every slot its own warp (config 1, 100 walkers: 30.7 us against 34.7 us mixed);
+// above it the queue balances better than waves of blocks.  Measured on config 2 (1024 walkers) against the
+// queue alone: repeated evaluations on a warm L2 (the sampler, host-API calls) gain -- MCMC 12.8 k -> 14.0 k
+// steps/s brute force, e2e 5.4e10 -> 5.8e10 wt/s, windowed step 46.0 -> 44.2 us -- while a brute-force step
+// on a flushed L2 loses 2.6 us (49.9 -> 52.5 us: three waves of direct blocks, each paying its cold misses).
+// NMB_MIXED_MINCW / NMB_MIXED_MAXCW override.
 static bool use_mixed(const nmb_lc* lc, size_t CW) {
     static const long long lo = std::getenv("NMB_MIXED_MINCW") ? std::atoll(std::getenv("NMB_MIXED_MINCW")) : 256;
     static const long long hi = std::getenv("NMB_MIXED_MAXCW") ? std::atoll(std::getenv("NMB_MIXED_MAXCW")) : 1184;
@@ -441,10 +445,10 @@ static bool use_mixed(const nmb_lc* lc, size_t CW) {
 }
 
 // Slots a direct block of eval_mixed_kernel takes: two per warp (six flux rounds).  A longer range in one
-// block would be the straggler of the launch (measured: three slots per warp = nine rounds, 13 us, against
-// 8 us for the rest) while queue workers run beside it and spread such walkers over the whole GPU.
-// window_direct_kernel takes one full pass per warp (`merge` slots): there the queue only starts after the
-// direct blocks, so fewer queued walkers is the better trade (config 1: 26.5 us against 32.7 us).
+// block makes it the straggler of the launch while queue workers run beside it and could spread that
+// walker over the whole GPU (config 1 with the mixed path forced: 40.4 us with three slots per warp, 34.7 us
+// with two).  window_direct_kernel takes one full pass per warp (`merge` slots): there the queue only
+// starts after the direct blocks, so fewer queued walkers is the better trade.
 static int direct_cap_slots(const nmb_lc* lc, bool queue_runs_beside) {
     static const int per_warp = std::getenv("NMB_DIRECT_SLOTS") ? std::max(1, std::atoi(std::getenv("NMB_DIRECT_SLOTS"))) : 2;
     return (kEvalThreads / 32) * (queue_runs_beside ? std::min(per_warp, lc->ws.merge) : lc->ws.merge);

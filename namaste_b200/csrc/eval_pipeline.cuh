@@ -276,6 +276,12 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
         const double* tr = sm.traw[buf];
         const double* tm = sm.term[buf];
         const int base = c * CH;
+        // stage 2 reads flux and weight of the in-transit timestamps, which this kernel never touches: the
+        // first walker group asks L2 for the chunk's lines now (16 B per timestamp, once per light curve)
+        if (wb == 0 && tid < 2 * (CH * 8 / 128)) {
+            const double* src = (tid & 1 ? lc.w : lc.f) + (long long)cand * lc.npad + base + (tid >> 1) * 16;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+        }
 #pragma unroll 2
         for (int i = 0; i < CH; ++i) {
             int qmin = INT_MAX;
