@@ -489,7 +489,7 @@ def run_ours(args):
         import multiprocessing as mp
         cores = len(os.sched_getaffinity(0))
         pool = mp.Pool(cores)
-        rate, nwalk, dt = cpu_reference_rate(wl, 12.0, pool, cores)
+        rate, nwalk, dt = cpu_reference_rate(wl, 24.0, pool, cores)  # lands at 10-15 s of CPU work
         pool.close()
         line["cpu_baseline"] = {"value": rate, "unit": "wt/s", "cores": cores, "kind": "port",
                                 "sample": "%d walker evaluations of the same workload (N=%d, S=%d) in %.1f s, "
