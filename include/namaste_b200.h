@@ -45,6 +45,10 @@ extern "C" {
 #define NMB_MODE_BRUTE 0    /* every fine sample of every timestamp is visited            */
 #define NMB_MODE_WINDOWED 1 /* exact: out-of-transit chi^2 from prefix sums, window only  */
 #define NMB_MODE_FUSED 2    /* brute force in one launch (small problems / diagnostics)     */
+/* Within a mode the library picks its kernels by ensemble size (a block per walker for small and mid-sized
+ * ensembles, a load-balanced slot queue otherwise; nmb_last_kernels reports the choice).  The choice never
+ * changes a result: slot boundaries and summation trees are the same on every path, so a walker's lnprob has
+ * the same bits whatever ensemble, launch shape or number of GPUs it is evaluated with. */
 
 /* GP noise-model kernels (namaste/namaste.py:279-314) */
 #define NMB_GP_REAL 0  /* celerite RealTerm(log_a, log_c) + JitterTerm(log_sigma)                    */
