@@ -448,6 +448,9 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[args.workload], "N": N, "S": S, "W": W,
                    "step": "one full-ensemble lnprob evaluation (likelihood + priors), brute-force kernel",
+                   "arithmetic": "NMB_F64: FP64 with contracted multiply-adds and <= 1.5-ulp quotients / roots in the two "
+                                 "hot occultation cases (lnprob within 1e-13 of the reference, tolerance 1e-10); the "
+                                 "reference's own rounding sequence is timed under 'strict'",
                    "parallelism": "independent candidate per GPU, no collective" if world > 1 else "single GPU",
                    "l2": "192 MiB buffer zeroed between timed iterations (inputs are 0.15 MB, L2/SMEM resident by design)"},
         "clocks": clk,
