@@ -38,7 +38,7 @@ def _fingerprint(a):
     bits = np.ascontiguousarray(a, dtype=np.float64).reshape(-1).view(np.uint64)
     odd = _ODD.get(bits.size)
     if odd is None:
-        if len(_ODD) > 16:
+        if len(_ODD) >= 4:   # a few light-curve lengths at most (12 MB per 500 k-point entry)
             _ODD.clear()
         odd = _ODD[bits.size] = (np.arange(bits.size, dtype=np.uint64) << np.uint64(1)) | np.uint64(1)
     return (a.__array_interface__["data"][0], a.shape, a.strides,
