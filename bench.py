@@ -1,14 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the Namaste likelihood hot path on B200 (driver contract: one JSON line).
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload k2|kepler|epic]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload auto|kepler|k2|epic|tess|batch]
 
-Metric (BASELINE.json): walker x timestamp log-probability evaluations per second.
-One *step* = one full-ensemble lnprob evaluation (W walkers x N timestamps x S supersamples,
-likelihood + priors) on synthetic input of BASELINE config 2 ("synthetic K2 long-cadence
-light curve, 4k points, supersampling x11, 1024 walkers").  With N > 1 GPUs every rank runs
-an independent candidate of that shape (the reference's batch-of-candidates mode: no data-path
-collective), so per-GPU work is fixed ("weak" scaling) and `value` is the sum over ranks.
+Metric (BASELINE.json): walker x timestamp log-probability evaluations per second (wt/s), and MCMC
+steps per second.  One *step* = one full-ensemble lnprob evaluation (likelihood + priors) of the
+workload on synthetic input of the BASELINE shape.
+
+Headline workload (`--workload auto`, the default):
+  N = 1 : BASELINE configs[2], the largest single-GPU configuration -- synthetic Kepler long cadence,
+          65 000 points, supersampling x15, 4096 walkers.
+  N > 1 : BASELINE configs[3], the batched-candidate configuration the north star asks to scale --
+          256 independent candidates (4000 points, 100 walkers each) per GPU, staged as one batch per
+          rank, no data-path collective; per-GPU work is fixed ("weak"), `value` sums over ranks.
+          The N = 1 line carries the same measurement of one GPU's share under `candidate_batch`.
+Every line also carries `walker_split`: BASELINE configs[4], ONE 16 384-walker ensemble on a 500 000-point
+light curve split by walker over the N ranks (strong scaling; at N = 1 the whole ensemble on one GPU),
+with the chain compared bit for bit against a single-GPU run inside the leg.
 
 `value`   : brute-force kernel (every supersample of every timestamp is visited and classified),
             inputs resident in HBM, CUDA-event timed per step with an L2 flush between steps.
@@ -16,9 +24,10 @@ collective), so per-GPU work is fixed ("weak" scaling) and `value` is the sum ov
             pinned H2D of the walker positions and D2H of the log-probabilities every step.
 `windowed`: the exact prefix-sum/window kernel (product default), reported separately and never
             as a roofline fraction.
-`roofline`: FP64-pipe bound; algorithmic FLOPs per SURVEY.md 8(d) convention / event time,
-            against a DFMA microbenchmark measured in the same process.
-`cpu_baseline`: the NumPy oracle (port of the reference's CPU path) on the host cores.
+`roofline`: FP64-pipe bound; `frac` = algorithmic FLOPs per SURVEY.md 8(d) convention / event time / peak,
+            `frac_executed` = FP64 instructions actually issued (x2 flops) / event time / peak; the
+            peak is a DFMA microbenchmark measured in the same process.
+`cpu_baseline`: the NumPy oracle (port of the reference's CPU path) on the host cores, pool and one core.
 """
 import argparse
 import json
@@ -40,24 +49,27 @@ WORKLOADS = {
     "epic": (1, 2828, 0.0204318, 2061.0, 5.4e-5, 10, 100),
     "tess": (5, 500000, 2.0 / 1440, 1325.0, 6e-4, 10, 2048),
 }
+BATCH_PER_GPU, BATCH_W, BATCH_N, BATCH_S = 256, 100, 4000, 11
+SPLIT_W = 16384
 WORKLOAD_DESC = {
     "k2": "BASELINE configs[1]: synthetic K2 long-cadence, N=4000, S=11, W=1024",
     "kepler": "BASELINE configs[2]: synthetic Kepler long-cadence, N=65000, S=15, W=4096",
     "epic": "BASELINE configs[0] shape: N=2828, S=10, W=100 (synthetic noise)",
     "tess": "BASELINE configs[4] per-GPU share: synthetic TESS 2-min, N=500000, S=10, W=2048",
+    "batch": "BASELINE configs[3]: independent single-transit candidates, N=4000, S=11, 100 walkers each, "
+             "256 candidates per GPU",
 }
+METRIC = "lnprob_walker_timestamp_evals_per_sec"
 
 
 # --------------------------------------------------------------------------------------------
-# synthetic workload (SURVEY.md 8d recipe).  The noiseless model is drawn with plain NumPy
-# geometry + the GPU model itself is NOT used here; the oracle is only needed for cpu_baseline.
+# synthetic workloads (SURVEY.md 8d recipe).  The injected transit is a box of depth p^2: timing does
+# not depend on the exact injected shape, and this keeps the GPU arm independent of oracle/.
 def make_workload(name, seed_offset=0):
     cfg, n, cad, t0, sigma, S, W = WORKLOADS[name]
     rng = np.random.default_rng(151203722 + cfg + 1000 * seed_offset)
     t = t0 + cad * np.arange(n)
     theta = np.array([t[n // 2] + 0.37 * cad, 0.5, 3.0, 0.06, 0.34, 0.30])
-    # box-shaped stand-in for the transit (depth p^2) + white noise: timing does not depend on the
-    # exact injected shape, and this keeps bench.py independent of oracle/ for the GPU arm
     z = np.sqrt(theta[1] ** 2 + (theta[2] * (t + 0.45 * cad - theta[0])) ** 2)
     flux = 1.0 - theta[3] ** 2 * (z < 1.0) + sigma * rng.standard_normal(n)
     lc = np.column_stack((t, flux, np.full(n, sigma)))
@@ -74,35 +86,61 @@ def make_workload(name, seed_offset=0):
     pos = theta[None, :] * (1 + 1e-3 * rng.standard_normal((W, 6)))
     nbox = max(1, W // 20)
     pos[:nbox] = ptab[:, 0] + (ptab[:, 1] - ptab[:, 0]) * rng.uniform(0, 1, (nbox, 6))
-    return dict(name=name, lc=lc, theta=theta, priors=ptab, pos=pos, S=S, W=W, N=n, cad=cad)
+    return dict(name=name, lc=lc, theta=theta, priors=ptab, pos=pos, S=S, W=W, N=n, cad=cad, C=1)
 
 
-def count_samples(wl):
-    """Per-ensemble counts for the FLOP formula of SURVEY.md 8(d): fine samples in total, interior
-    (planet inside the disc) and ingress/egress samples, and timestamps with at least one
+def make_batch(rank, ncand=BATCH_PER_GPU, world=1):
+    """One GPU's share of BASELINE configs[3]: `ncand` independent candidates (global index
+    rank + world * k, the round-robin deal of namaste_b200.distributed.shard_candidates), each a 4000-point
+    K2-like light curve with its own transit (b, vel, RpRs jittered per SURVEY 8d), priors and a
+    100-walker ensemble (tight ball around its truth)."""
+    W, N, S = BATCH_W, BATCH_N, BATCH_S
+    curves, pos, tabs = [], [], []
+    for k in range(ncand):
+        gidx = rank + world * k
+        wl = make_workload("k2", seed_offset=gidx)
+        rng = np.random.default_rng(7 + gidx)
+        th = wl["theta"].copy()
+        th[1], th[2], th[3] = rng.uniform(0, 0.9), rng.uniform(1.5, 6.0), rng.uniform(0.03, 0.15)
+        t = wl["lc"][:, 0]
+        z = np.sqrt(th[1] ** 2 + (th[2] * (t + 0.45 * wl["cad"] - th[0])) ** 2)
+        lc = wl["lc"].copy()
+        lc[:, 1] = 1.0 - th[3] ** 2 * (z < 1.0) + 5.4e-5 * rng.standard_normal(N)
+        curves.append(lc)
+        pos.append(th[None, :] * (1 + 1e-3 * rng.standard_normal((W, 6))))
+        tab = wl["priors"].copy()
+        tab[2, 1], tab[2, 3], tab[2, 4] = th[2] * 1.6, th[2] * 1.1, th[2] * 0.12
+        tabs.append(tab)
+    return dict(name="batch", curves=curves, lc=None, pos=np.stack(pos), priors=np.stack(tabs), S=S, W=W, N=N,
+                C=ncand, cad=0.0204318)
+
+
+def count_samples_one(lc, pos, S, cad):
+    """Counts for the FLOP formula of SURVEY.md 8(d) over one ensemble on one light curve: interior
+    (planet inside the disc) and ingress/egress fine samples, and timestamps with at least one
     in-transit sample (those are evaluated by stage 2, the others by stage 1 alone)."""
-    t, S, cad = wl["lc"][:, 0], wl["S"], wl["cad"]
+    t = lc[:, 0]
     off = cad * np.arange(0, 1.0, 1 / S)
     m_int = m_edge = t_in = 0
-    for par in wl["pos"]:
+    for par in pos:
         tcen, b, vel, rp = par[0], par[1], par[2], abs(par[3])
         h2 = (1 + rp) ** 2 - b * b
         if h2 <= 0:
             continue
         if vel == 0:
-            sel = np.arange(len(t))
+            i0, i1 = 0, len(t)
         else:
             half = np.sqrt(h2) / abs(vel) + 2 * cad
-            sel = np.where(np.abs(t - tcen) < half)[0]
-        if len(sel) == 0:
+            i0, i1 = np.searchsorted(t, tcen - half), np.searchsorted(t, tcen + half)
+        if i1 <= i0:
             continue
-        z = np.sqrt(b * b + (vel * ((t[sel, None] + off[None, :]) - tcen)) ** 2)
+        z = np.sqrt(b * b + (vel * ((t[i0:i1, None] + off[None, :]) - tcen)) ** 2)
         inner = z < abs(1 - rp)
         limb = (z < 1 + rp) & ~inner
         m_int += int(np.sum(inner))
         m_edge += int(np.sum(limb))
         t_in += int(np.sum(np.any(inner | limb, axis=1)))
-    return wl["W"] * wl["N"] * S, m_int, m_edge, t_in
+    return m_int, m_edge, t_in
 
 
 def algorithmic_flops(wl):
@@ -111,11 +149,29 @@ def algorithmic_flops(wl):
     visits every fine sample and closes the out-of-transit timestamps, stage 2 adds the in-transit
     terms, the residuals of the in-transit timestamps and the priors (its recomputation of z for
     those samples is implementation work and is not counted)."""
-    m, m_int, m_edge, t_in = count_samples(wl)
-    wn = wl["W"] * wl["N"]
+    m_int = m_edge = t_in = 0
+    if wl["C"] == 1:
+        m_int, m_edge, t_in = count_samples_one(wl["lc"], wl["pos"], wl["S"], wl["cad"])
+    else:
+        for lc, pos in zip(wl["curves"], wl["pos"]):
+            cad = float(np.median(np.diff(lc[:, 0])))
+            a, b, c = count_samples_one(lc, pos, wl["S"], cad)
+            m_int, m_edge, t_in = m_int + a, m_edge + b, t_in + c
+    wn = wl["C"] * wl["W"] * wl["N"]
+    m = wn * wl["S"]
     sweep = m * 7 + (wn - t_in) * 5
-    evalk = m_int * 143 + m_edge * 180 + t_in * 5 + wl["W"] * 40
+    evalk = m_int * 143 + m_edge * 180 + t_in * 5 + wl["C"] * wl["W"] * 40
     return sweep + evalk, sweep, evalk, (m, m_int, m_edge, t_in)
+
+
+# FP64 instructions the kernels actually issue (per lane), counted on the ncu source pages of round 1
+# (DESIGN.md section 4): the sweep issues 2 DFMA per fine sample and one DADD per timestamp; the relaxed
+# stage 2 issues about 210 FP64 instructions per in-transit fine sample plus ~40 per in-transit timestamp
+# (bin mean, residual, term) -- an estimate for stage 2, exact for the sweep.
+def executed_fp64(wl, counts):
+    m, m_int, m_edge, t_in = counts
+    wn = wl["C"] * wl["W"] * wl["N"]
+    return 2 * m + wn, 210 * (m_int + m_edge) + 40 * t_in
 
 
 # --------------------------------------------------------------------------------------------
@@ -167,10 +223,12 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
+# CPU side: the NumPy oracle (port of the reference's CPU path).  The only place bench.py touches oracle/.
 def _oracle_walker(args):
     from oracle import namaste_oracle as o
     par, lc, pri, S = args
-    return o.mono_only_logprob(par, lc, pri, S)
+    with np.errstate(all="ignore"):
+        return o.mono_only_logprob(par, lc, pri, S)
 
 
 def _priors_dict(tab):
@@ -180,326 +238,529 @@ def _priors_dict(tab):
             for nm, r in zip(names, tab)}
 
 
-def cpu_reference_rate(wl, budget_s, pool, cores, nwalk=None):
-    """wt/s of the NumPy oracle (the reference's CPU path restated) on `cores` processes."""
-    pri = _priors_dict(wl["priors"])
-    W = wl["W"]
-    pool.map(_oracle_walker, [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(cores)])  # imports
+def _cpu_jobs(wl, nwalk):
+    """`nwalk` walker evaluations of the workload, cycling through its ensemble (and candidates)."""
+    S = wl["S"]
+    if wl["C"] == 1:
+        pri = _priors_dict(wl["priors"])
+        return [(wl["pos"][i % wl["W"]], wl["lc"], pri, S) for i in range(nwalk)]
+    jobs = []
+    for i in range(nwalk):
+        c, w = i % wl["C"], (i // wl["C"]) % wl["W"]
+        jobs.append((wl["pos"][c][w], wl["curves"][c], _priors_dict(wl["priors"][c]), S))
+    return jobs
+
+
+def cpu_pool_rate(wl, pool, cores, nwalk):
+    jobs = _cpu_jobs(wl, nwalk)
     t0 = time.perf_counter()
-    pool.map(_oracle_walker, [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(cores)])
-    per_walker = (time.perf_counter() - t0)  # one walker per core, in parallel
-    if nwalk is None:
-        nwalk = int(max(cores, min(64 * W, budget_s / max(per_walker, 1e-6) * cores)))
-    jobs = [(wl["pos"][i % W], wl["lc"], pri, wl["S"]) for i in range(nwalk)]
-    t0 = time.perf_counter()
-    pool.map(_oracle_walker, jobs, chunksize=max(1, nwalk // (cores * 4)))
+    if pool is None:
+        for j in jobs:
+            _oracle_walker(j)
+    else:
+        pool.map(_oracle_walker, jobs, chunksize=max(1, nwalk // (cores * 4)))
     dt = time.perf_counter() - t0
-    return nwalk * wl["N"] / dt, nwalk, dt
+    return nwalk * wl["N"] / dt, dt
+
+
+def cpu_probe(wl, pool, cores):
+    """seconds per walker evaluation on one core (one job per core in parallel, after the imports)."""
+    pool.map(_oracle_walker, _cpu_jobs(wl, cores))
+    t0 = time.perf_counter()
+    pool.map(_oracle_walker, _cpu_jobs(wl, cores))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, budget_s=18.0, reps=3):
+    """The reference's CPU path beside the GPU numbers: process pool on all host
+    cores and a single process, >= 3 repetitions each, best and median; a bounded subset of the ensemble
+    scaled linearly (stated)."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    pool = mp.Pool(cores)
+    per = cpu_probe(wl, pool, cores)
+    total_w = wl["C"] * wl["W"]
+    nwalk = int(max(cores, min(total_w, (budget_s * 0.75 / reps) / max(per, 1e-6) * cores)))
+    rates, secs = [], 0.0
+    for _ in range(reps):
+        r, dt = cpu_pool_rate(wl, pool, cores, nwalk)
+        rates.append(r); secs += dt
+    pool.close()
+    n1 = int(max(2, min(64, (budget_s * 0.25 / reps) / max(per, 1e-6))))
+    r1, s1 = [], 0.0
+    _oracle_walker(_cpu_jobs(wl, 1)[0])
+    for _ in range(reps):
+        r, dt = cpu_pool_rate(wl, None, 1, n1)
+        r1.append(r); s1 += dt
+    return {"value": max(rates), "median": float(np.median(rates)), "unit": "wt/s", "cores": cores, "kind": "port",
+            "repetitions": reps,
+            "sample": "%d of %d walker evaluations per repetition (full N=%d, S=%d), scaled linearly; NumPy oracle in a "
+                      "%d-process pool (like emcee threads=, namaste.py:590); %.1f s of CPU work" % (
+                          nwalk, total_w, wl["N"], wl["S"], cores, secs),
+            "single_core": {"value": max(r1), "median": float(np.median(r1)), "unit": "wt/s", "cores": 1,
+                            "sample": "%d walker evaluations per repetition, %d repetitions, %.1f s" % (n1, reps, s1)}}
+
+
+def pick_workload(args):
+    name = args.workload
+    if name == "auto":
+        name = "kepler" if args.gpus == 1 else "batch"
+    return name
+
+
+def workload_config(name, wl, world):
+    """`config` of the JSON line: identical for our arm and the reference arm."""
+    return {"workload": WORKLOAD_DESC[name], "N": wl["N"], "S": wl["S"], "W": wl["W"], "candidates_per_gpu": wl["C"],
+            "step": "one full-ensemble lnprob evaluation (likelihood + priors) of every candidate",
+            "parallelism": ("independent candidates dealt to %d GPUs, no collective" % world) if world > 1 else "single GPU"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (NumPy oracle port,
     multiprocessing pool like emcee's threads=) on this box's host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     import multiprocessing as mp
-    wl = make_workload(args.workload)
+    name = pick_workload(args)
+    wl = make_batch(0, world=world) if name == "batch" else make_workload(name)
     cores = len(os.sched_getaffinity(0))
     pool = mp.Pool(cores)
-    # size each step so that warmup+steps finish within ~2 minutes
-    pri = _priors_dict(wl["priors"])
-    pool.map(_oracle_walker, [(wl["pos"][i % wl["W"]], wl["lc"], pri, wl["S"]) for i in range(cores)])  # imports
-    t0 = time.perf_counter()
-    pool.map(_oracle_walker, [(wl["pos"][i % wl["W"]], wl["lc"], pri, wl["S"]) for i in range(cores)])
-    per = time.perf_counter() - t0
+    per = cpu_probe(wl, pool, cores)
     total_steps = args.steps + args.warmup
-    nwalk = int(max(cores, min(wl["W"], (100.0 / total_steps) / max(per, 1e-6) * cores)))
+    total_w = wl["C"] * wl["W"]
+    # size each step so that warmup + steps finish within ~100 s
+    nwalk = int(max(cores, min(total_w, (100.0 / total_steps) / max(per, 1e-6) * cores)))
     for _ in range(args.warmup):
-        cpu_reference_rate(wl, 0, pool, cores, nwalk=nwalk)
+        cpu_pool_rate(wl, pool, cores, nwalk)
     t_begin = time.perf_counter()
-    rates = []
     for _ in range(args.steps):
-        r, _, _ = cpu_reference_rate(wl, 0, pool, cores, nwalk=nwalk)
-        rates.append(r)
+        cpu_pool_rate(wl, pool, cores, nwalk)
     elapsed = time.perf_counter() - t_begin
     pool.close()
     value = args.steps * nwalk * wl["N"] / elapsed
-    sample = "%d of %d walkers per step (full N=%d, S=%d), NumPy oracle in a %d-process pool" % (
-        nwalk, wl["W"], wl["N"], wl["S"], cores)
+    sample = "%d of %d walker evaluations per step (full N=%d, S=%d), NumPy oracle in a %d-process pool" % (
+        nwalk, total_w, wl["N"], wl["S"], cores)
     line = {
-        "impl": "reference", "metric": "lnprob_walker_timestamp_evals_per_sec", "value": value, "unit": "wt/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "wt/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload], "sample": sample},
+        "config": workload_config(name, wl, args.gpus),
         "cpu_baseline": {"value": value, "unit": "wt/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "wt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "host CPU rate of ONE box; it does not grow with --gpus (the reference has no GPU path)",
     }
     _emit(line)
 
 
 # --------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import namaste_b200 as nb
+class Bench(object):
+    """Device-side measurement helpers shared by the legs."""
 
-    wl = make_workload(args.workload, seed_offset=rank)
-    W, N, S = wl["W"], wl["N"], wl["S"]
-    staged = nb.LightCurve(wl["lc"], oversamp=S)
-    d_pos = torch.from_numpy(wl["pos"]).cuda()
-    d_pri = torch.from_numpy(wl["priors"]).cuda()[None].contiguous()
-    out = torch.empty((1, W), dtype=torch.float64, device="cuda")
-    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        import namaste_b200 as nb
+        self.nb = nb
+        self.flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+        self.stream = torch.cuda.current_stream()
+        self.noflush = bool(os.environ.get("NMB_BENCH_NOFLUSH"))
 
-    def device_loop(mode, steps, sampler=None):
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        tt = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def device_loop(self, fn, steps):
+        """`steps` calls of fn(), each between two CUDA events on the launching stream, L2 flushed before
+        each (not timed); barrier + synchronize on both sides.  Returns the per-step times in ms."""
+        torch = self.torch
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        if world > 1:
-            dist.barrier()
+        self.barrier()
         torch.cuda.synchronize()
         t_begin = time.perf_counter()
         for e0, e1 in evs:
-            if not os.environ.get('NMB_BENCH_NOFLUSH'):
-                flush.zero_()                  # L2 flush between timed iterations (not timed)
-            e0.record(stream)
-            staged.lnprob_device(d_pos, d_pri, out=out, mode=mode)
-            e1.record(stream)
+            if not self.noflush:
+                self.flush.zero_()
+            e0.record(self.stream)
+            fn()
+            e1.record(self.stream)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        self.barrier()
         t_end = time.perf_counter()
-        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        return ms, t_begin, t_end
+        return np.array([e0.elapsed_time(e1) for e0, e1 in evs]), t_begin, t_end
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+    def host_loop(self, fn, steps):
+        self.barrier()
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        dt = time.perf_counter() - t0
+        return self.max_over_ranks(dt), res
 
-    # ---- device-resident measurement (brute force = `value`) ---------------------------------
-    device_loop("brute", max(args.warmup, 3))
-    clocks = ClockSampler(local)
-    clocks.start()
+
+def stage(nb, wl):
+    return nb.LightCurve(wl["curves"] if wl["C"] > 1 else wl["lc"], oversamp=wl["S"])
+
+
+def measure_lnprob(b, wl, staged, steps, warmup, with_clocks=False, variants=True):
+    """Device-resident brute-force (`value`) and windowed evaluation, per-kernel split, end-to-end host API."""
+    torch, nb = b.torch, b.nb
+    C, W, N = wl["C"], wl["W"], wl["N"]
+    units = C * W * N * b.world
+    d_pos = torch.from_numpy(np.ascontiguousarray(wl["pos"])).cuda()
+    ptab = wl["priors"] if wl["priors"].ndim == 3 else wl["priors"][None]
+    d_pri = torch.from_numpy(np.ascontiguousarray(ptab)).cuda()
+    out = torch.empty((C, W), dtype=torch.float64, device="cuda")
+    res = {}
+
+    def ev(mode, dtype="f64"):
+        return lambda: staged.lnprob_device(d_pos, d_pri, out=out, mode=mode, dtype=dtype)
+
+    b.device_loop(ev("brute"), warmup)
+    clocks = None
+    if with_clocks:
+        clocks = ClockSampler(b.local)
+        clocks.start()
     l0 = nb.launch_count()
-    ms_brute, t_b, t_e = device_loop("brute", args.steps)
-    launches = nb.launch_count() - l0
-    # keep the same loop running ~1 s longer so nvidia-smi (100 ms period) sees it under load
-    t_stop = time.perf_counter() + (0.0 if args.profile else 1.0)
-    while time.perf_counter() < t_stop:
-        for _ in range(200):
-            staged.lnprob_device(d_pos, d_pri, out=out, mode="brute")
-        torch.cuda.synchronize()
-    clk = clocks.stop(t_b, time.perf_counter())
-    ms_brute = max_over_ranks(ms_brute)
+    ms, t_b, t_e = b.device_loop(ev("brute"), steps)
+    res["launches"] = nb.launch_count() - l0
+    if with_clocks:
+        # keep the same loop running ~1 s longer so nvidia-smi (100 ms period) sees it under load
+        t_stop = time.perf_counter() + (0.0 if b.args.profile else 1.0)
+        while time.perf_counter() < t_stop:
+            for _ in range(max(1, int(20 / max(ms.mean(), 0.02)))):
+                ev("brute")()
+            torch.cuda.synchronize()
+        res["clocks"] = clocks.stop(t_b, time.perf_counter())
+    tot = b.max_over_ranks(float(ms.sum()))
+    res["brute"] = {"value": units / (tot / steps * 1e-3), "unit": "wt/s", "ms_per_step": tot / steps,
+                    "ms_per_step_median": b.max_over_ranks(float(np.median(ms))),
+                    "ms_per_step_min": float(ms.min()), "ms_per_step_max": float(ms.max())}
     # per-kernel durations of the same loop (CUDA events between the two kernels of every step)
     staged.stage_timing(True)
-    device_loop("brute", args.steps)
-    ms_s1, ms_s2, _ = staged.stage_times()
-    k_s1, k_s2 = staged.last_kernels()   # stage 2 is eval_mixed_kernel or eval_slots_kernel, by ensemble size
+    b.device_loop(ev("brute"), steps)
+    res["stage_ms"] = staged.stage_times()[:2]
+    res["kernels"] = staged.last_kernels()
     staged.stage_timing(False)
-    device_loop("windowed", max(args.warmup, 3))
-    ms_win, _, _ = device_loop("windowed", args.steps)
-    ms_win = max_over_ranks(ms_win)
-    ref_f64 = out.cpu().numpy().copy()
-    # FP32 variant (reported separately): windowed stage 1 + FP32 transit model in stage 2
-    def device_loop_dtype(steps, dtype, mode="windowed"):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        torch.cuda.synchronize()
-        for e0, e1 in evs:
-            flush.zero_()
-            e0.record(stream)
-            staged.lnprob_device(d_pos, d_pri, out=out, mode=mode, dtype=dtype)
-            e1.record(stream)
-        torch.cuda.synchronize()
-        return sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    fin = np.isfinite(ref_f64) & (np.abs(ref_f64) < 1e15)
-    device_loop_dtype(max(args.warmup, 3), "f32")
-    ms_f32 = max_over_ranks(device_loop_dtype(args.steps, "f32"))
-    f32_out = out.cpu().numpy().copy()
-    f32_err = float(np.max(np.abs(f32_out[fin] - ref_f64[fin]) / np.abs(ref_f64[fin])))
-    # strict variant (the reference's own rounding sequence in the hot occultation cases), brute force
-    device_loop_dtype(max(args.warmup, 3), "strict", "brute")
-    ms_strict = max_over_ranks(device_loop_dtype(args.steps, "strict", "brute"))
-    strict_out = out.cpu().numpy().copy()
-    strict_diff = float(np.max(np.abs(strict_out[fin] - ref_f64[fin]) / np.abs(ref_f64[fin])))
-    staged.lnprob_device(d_pos, d_pri, out=out, mode="windowed")  # leave the FP64 result in `out`
+    b.device_loop(ev("windowed"), warmup)
+    msw, _, _ = b.device_loop(ev("windowed"), steps)
+    totw = b.max_over_ranks(float(msw.sum()))
     ref_out = out.cpu().numpy().copy()
+    res["windowed"] = {"value": units / (totw / steps * 1e-3), "unit": "wt/s", "ms_per_step": totw / steps,
+                       "ms_per_step_median": b.max_over_ranks(float(np.median(msw))),
+                       "speedup_vs_brute": tot / totw, "kernels": list(staged.last_kernels()),
+                       "note": "exact prefix-sum + in-transit-window kernel; effective wt/s, not a roofline figure"}
+    fin = np.isfinite(ref_out) & (np.abs(ref_out) < 1e15)
+    if variants:
+        short = max(3, min(steps, 10))
+        for key, dtype, mode in (("fp32", "f32", "windowed"), ("strict", "strict", "brute")):
+            b.device_loop(ev(mode, dtype), 3)
+            msv, _, _ = b.device_loop(ev(mode, dtype), short)
+            vout = out.cpu().numpy().copy()
+            res[key] = {"value": units / (b.max_over_ranks(float(msv.sum())) / short * 1e-3), "unit": "wt/s",
+                        "ms_per_step": float(msv.mean()), "mode": mode,
+                        "max_rel_diff_vs_default_f64": float(np.max(np.abs(vout[fin] - ref_out[fin]) / np.abs(ref_out[fin])))}
+    # ---- end to end through the public host API (numpy in / numpy out) --------------------
+    pos_h, pri_h = np.ascontiguousarray(wl["pos"]), np.ascontiguousarray(wl["priors"])
+    for mode in ("brute", "windowed"):
+        b.host_loop(lambda: staged.lnprob(pos_h, pri_h, mode=mode), warmup)
+        dt, got = b.host_loop(lambda: staged.lnprob(pos_h, pri_h, mode=mode), steps)
+        assert np.allclose(np.asarray(got).reshape(ref_out.shape), ref_out, rtol=1e-12, atol=0, equal_nan=True), mode
+        res["e2e_" + mode] = {"value": units / (dt / steps), "unit": "wt/s", "ms_per_step": 1e3 * dt / steps}
+    res["h2d"] = int(pos_h.size * 8 + ptab.size * 8)
+    res["d2h"] = int(C * W * 8)
+    res["ref_out"] = ref_out
+    return res
 
-    # ---- end to end through the public host API (numpy in / numpy out) -----------------------
-    def e2e_loop(mode, steps):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            res = staged.lnprob(wl["pos"], wl["priors"], mode=mode)
-        dt = time.perf_counter() - t0
-        return max_over_ranks(dt), res
 
-    e2e_loop("brute", max(args.warmup, 3))
-    dt_e2e, res_host = e2e_loop("brute", args.steps)
-    e2e_loop("windowed", max(args.warmup, 3))
-    dt_e2e_win, res_host_w = e2e_loop("windowed", args.steps)
-    assert np.allclose(res_host_w, ref_out[0], rtol=1e-12, atol=0, equal_nan=True)
-    assert np.allclose(res_host, ref_out[0], rtol=1e-12, atol=0, equal_nan=True)
-
-    # ---- MCMC steps/s with the device-resident sampler (proposal + lnprob + accept on the GPU) ---
-    mcmc = {}
-    n_mcmc = 20 if args.profile else 200
-    for mode in ("windowed", "brute"):
-        smp = nb.EnsembleSampler(W, 6, nb.MonoOnlyLogProb, args=(staged, wl["priors"]), mode=mode, seed=1 + rank)
+def measure_mcmc(b, wl, staged, n_mcmc, modes=("windowed", "brute")):
+    """MCMC steps/s with the device-resident sampler (proposal + lnprob + accept on the GPU)."""
+    nb, torch = b.nb, b.torch
+    C, W, N = wl["C"], wl["W"], wl["N"]
+    out = {}
+    for mode in modes:
+        smp = nb.EnsembleSampler(W, 6, nb.MonoOnlyLogProb, args=(staged, wl["priors"]), mode=mode, seed=1 + b.rank)
         smp.run_mcmc(wl["pos"], n_mcmc)     # warm-up: also grows the device-resident chain to its final capacity
         smp.reset()
-        if world > 1:
-            dist.barrier()
+        b.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         smp.run_mcmc(None, n_mcmc)          # returns after the device finished and pos/lnprob were read back
-        dt = max_over_ranks(time.perf_counter() - t0)
-        mcmc[mode] = {"steps_per_s": n_mcmc / dt, "wt_per_s": n_mcmc * W * N * world / dt,
-                      "acceptance": float(smp.acceptance_fraction.mean())}
+        dt = b.max_over_ranks(time.perf_counter() - t0)
+        out[mode] = {"steps_per_s": n_mcmc / dt, "candidate_steps_per_s": n_mcmc * C * b.world / dt,
+                     "wt_per_s": n_mcmc * C * W * N * b.world / dt, "acceptance": float(smp.acceptance_fraction.mean())}
         del smp
+    out["steps"] = n_mcmc
+    out["note"] = "one step = every walker of every candidate proposed once (two half-ensemble phases); chain kept in HBM"
+    return out
 
-    # ---- GP noise-model objective (the reference's default, MonoLogProb): reported separately ----------
-    import ctypes
-    from namaste_b200._lib import load as _load, check as _check, ptr as _ptr
-    kfix = np.array([np.log(np.var(wl["lc"][:, 1])), -np.log(3.0), np.log(np.median(wl["lc"][:, 2]))])
-    gp_pos = np.hstack([kfix[None, :2] + 0.1 * np.random.default_rng(3 + rank).standard_normal((W, 2)), wl["pos"]])
-    d_gp = torch.from_numpy(np.ascontiguousarray(gp_pos)).cuda()
-    d_kfix = kfix.copy()
-    gp_out = torch.empty((1, W), dtype=torch.float64, device="cuda")
 
-    def gp_loop(steps):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        torch.cuda.synchronize()
-        for e0, e1 in evs:
-            flush.zero_()
-            e0.record(stream)
-            _check(_load().nmb_gp_lnprob(staged._h, _ptr(d_gp), W, 0, _ptr(d_kfix), 3, None, _ptr(gp_out), None,
-                                         ctypes.c_void_p(stream.cuda_stream)), "gp")
-            e1.record(stream)
-        torch.cuda.synchronize()
-        return sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    gp_steps = max(3, min(args.steps, 20))
-    gp_loop(3)
-    ms_gp = max_over_ranks(gp_loop(gp_steps)) / gp_steps
+def roofline_of(b, wl, res, peak_tf, traffic):
+    flops, fl_sweep, fl_eval, counts = algorithmic_flops(wl)
+    ex_sweep, ex_eval = executed_fp64(wl, counts)
+    ms_s1, ms_s2 = res["stage_ms"]
+    k_s1, k_s2 = res["kernels"]
+    kernels = []
+    for name, ms, fl, ex in ((k_s1, ms_s1, fl_sweep, ex_sweep), (k_s2, ms_s2, fl_eval, ex_eval)):
+        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        tfx = 2.0 * ex / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        kernels.append({"kernel": name, "ms_per_launch": ms,
+                        "share_of_step": ms / (ms_s1 + ms_s2) if ms_s1 + ms_s2 > 0 else None,
+                        "flops_per_launch": fl, "achieved": tf, "frac": tf / peak_tf,
+                        "executed_fp64_instr_per_launch": ex, "achieved_executed": tfx, "frac_executed": tfx / peak_tf,
+                        "traffic": traffic.get(name)})
+    dom = max(kernels, key=lambda k: k["ms_per_launch"])
+    step_s = res["brute"]["ms_per_step"] * 1e-3
+    m, m_int, m_edge, t_in = counts
+    return {"bound": "fp64", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": dom["frac"], "frac_executed": dom["frac_executed"],
+            "achieved_executed": dom["achieved_executed"], "traffic": dom["traffic"],
+            "traffic_source": "profiles/traffic.json (ncu --set full capture of a previous run, dram bytes read + written "
+                              "per launch), not measured in this run",
+            "peak_source": "DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 entry)",
+            "flops_convention": "frac: SURVEY.md 8(d) -- 7/fine sample + 143 interior + 180 ingress + 5/timestamp + 40/walker; "
+                                "frac_executed: FP64 instructions issued per lane x 2 flops (sweep: 2 DFMA per fine sample + "
+                                "1 DADD per timestamp, exact; stage 2: ~210 per in-transit sample, from the ncu source pages)",
+            "fine_samples": m, "interior": m_int, "edge": m_edge, "in_transit_timestamps": t_in,
+            "kernels": kernels,
+            "whole_step": {"flops": flops, "ms": res["brute"]["ms_per_step"], "achieved": flops / step_s / 1e12,
+                           "frac": flops / step_s / 1e12 / peak_tf,
+                           "frac_executed": 2.0 * (ex_sweep + ex_eval) / step_s / 1e12 / peak_tf},
+            "note": "dominant kernel = the longer of the two launches of a brute-force step; per-kernel durations from "
+                    "CUDA events between the kernels (they do not overlap while measured)"}
 
-    # ---- one ensemble split by walker over the ranks (BASELINE config 5), NCCL all-gather per half-step ----
-    split = None
-    if world > 1 and not args.profile:
-        from namaste_b200.distributed import SplitEnsembleSampler
-        wl5 = make_workload("tess")
-        W5 = 16384
-        rng5 = np.random.default_rng(5)      # same ensemble on every rank (replicated, then sliced)
-        pos5 = wl5["theta"][None, :] * (1 + 1e-3 * rng5.standard_normal((W5, 6)))
-        lc5 = nb.LightCurve(wl5["lc"], oversamp=wl5["S"])
-        sp = SplitEnsembleSampler(lc5, wl5["priors"], W5, seed=77)
-        sp.run_mcmc(pos5, 3, storechain=False)
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n5 = 20
-        sp.run_mcmc(None, n5, storechain=False)
-        dt5 = max_over_ranks(time.perf_counter() - t0)
-        split = {"steps_per_s": n5 / dt5, "wt_per_s": n5 * W5 * wl5["N"] / dt5, "walkers": W5, "N": wl5["N"], "S": wl5["S"],
-                 "scaling": "strong", "collective": "NCCL all-gather of the updated half-ensemble slices, twice per step",
-                 "note": "BASELINE configs[4]: synthetic TESS 2-min light curve, one 16384-walker ensemble split by walker"}
-        del sp, lc5
+
+def measure_split(b, n_steps=20, n_check=3):
+    """BASELINE configs[4]: one 16384-walker ensemble on the 500 k-point light curve, split by walker over
+    the ranks (the whole ensemble on one GPU at N = 1).  The split chain is compared bit for bit with a
+    single-GPU run of the same seed inside the leg (rank 0), and the replicas are compared across ranks."""
+    nb, torch, dist = b.nb, b.torch, b.dist
+    from namaste_b200.distributed import SplitEnsembleSampler
+    wl5 = make_workload("tess")
+    W5 = SPLIT_W
+    rng5 = np.random.default_rng(5)      # same ensemble on every rank (replicated, then sliced)
+    pos5 = wl5["theta"][None, :] * (1 + 1e-3 * rng5.standard_normal((W5, 6)))
+    lc5 = nb.LightCurve(wl5["lc"], oversamp=wl5["S"])
+    out = {"walkers": W5, "N": wl5["N"], "S": wl5["S"], "scaling": "strong", "n_gpus": b.world,
+           "note": "BASELINE configs[4]: synthetic TESS 2-min light curve, one 16384-walker ensemble split by walker"}
+    sp = SplitEnsembleSampler(lc5, wl5["priors"], W5, seed=77)
+    out["transport"] = getattr(sp, "transport", "nccl")
+    p_split, l_split = sp.run_mcmc(pos5, n_check, storechain=False)
+    # replicas agree across ranks?
+    digest = np.array([np.bitwise_xor.reduce(p_split.view(np.uint64).ravel()),
+                       np.bitwise_xor.reduce(l_split.view(np.uint64).ravel())], dtype=np.uint64).view(np.int64)
+    same = True
+    if b.world > 1:
+        t = torch.from_numpy(digest.copy()).cuda()
+        lst = [torch.empty_like(t) for _ in range(b.world)]
+        dist.all_gather(lst, t)
+        same = all(bool(torch.equal(x, lst[0])) for x in lst)
+    out["replicas_identical"] = bool(same)
+    if b.rank == 0:
+        single = nb.EnsembleSampler(W5, 6, nb.MonoOnlyLogProb, args=(lc5, wl5["priors"]), seed=77)
+        p1, l1, _ = single.run_mcmc(pos5, n_check, storechain=False)
+        out["bitwise_equal"] = bool(np.array_equal(p1, p_split) and np.array_equal(l1, l_split))
+        out["checked_steps"] = n_check
+        del single
+    b.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sp.run_mcmc(None, n_steps, storechain=False)
+    dt = b.max_over_ranks(time.perf_counter() - t0)
+    out.update({"steps": n_steps, "steps_per_s": n_steps / dt, "ms_per_step": 1e3 * dt / n_steps,
+                "wt_per_s": n_steps * W5 * wl5["N"] / dt})
+    del sp, lc5
+    return out
+
+
+def measure_config1(b):
+    """BASELINE configs[0]: the real EPIC 203311200 light curve after the reference's mask (2828 points,
+    committed fixture generated from the reference's ExampleData), 100 walkers, S = 10."""
+    nb = b.nb
+    g = np.load(os.path.join(ROOT, "tests", "golden", "config1_epic203311200.npz"))
+    wl = dict(name="epic", lc=g["lc"], pos=g["walkers"], priors=g["priors"], S=10, W=len(g["walkers"]), N=len(g["lc"]), C=1,
+              cad=float(np.median(np.diff(g["lc"][:, 0]))))
+    staged = stage(nb, wl)
+    r = measure_lnprob(b, wl, staged, 20, 5, variants=False)
+    m = measure_mcmc(b, wl, staged, 200, modes=("windowed",))
+    out = {"workload": "BASELINE configs[0]: EPIC 203311200 (ExampleData light curve, reference mask), N=%d, S=10, W=%d" % (wl["N"], wl["W"]),
+           "brute": r["brute"], "windowed": r["windowed"], "e2e_brute": r["e2e_brute"], "e2e_windowed": r["e2e_windowed"],
+           "mcmc_windowed": m["windowed"]}
+    staged.close()
+    return out, wl
+
+
+def cpu_config1_mcmc(wl, nsteps=6):
+    """The reference's CPU run beside config 1: oracle likelihood + the stretch move of emcee as restated in
+    oracle/stretch_oracle.py, lnprob of a half-ensemble mapped over a process pool like emcee's threads=
+    (namaste.py:590-594)."""
+    import multiprocessing as mp
+    from oracle import stretch_oracle as so
+    cores = len(os.sched_getaffinity(0))
+    pool = mp.Pool(cores)
+    pri = _priors_dict(wl["priors"])
+
+    def lnp(p):
+        return np.array(pool.map(_oracle_walker, [(row, wl["lc"], pri, wl["S"]) for row in p]))
+    so.run(lnp, wl["pos"], 1, 1)
+    t0 = time.perf_counter()
+    so.run(lnp, wl["pos"], nsteps, 1)
+    dt = time.perf_counter() - t0
+    pool.close()
+    return {"steps_per_s": nsteps / dt, "wt_per_s": nsteps * wl["W"] * wl["N"] / dt, "cores": cores, "steps": nsteps,
+            "kind": "port", "note": "NumPy oracle lnprob + CPU stretch move (emcee restated), process pool over walkers"}
+
+
+def run_ours(args):
+    b = Bench(args)
+    torch, dist, nb = b.torch, b.dist, b.nb
+    rank, world = b.rank, b.world
+    name = pick_workload(args)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    wl = make_batch(rank, world=world) if name == "batch" else make_workload(name, seed_offset=rank)
+    staged = stage(nb, wl)
+    head = measure_lnprob(b, wl, staged, steps, warmup, with_clocks=True)
+    n_mcmc = 20 if args.profile else (50 if name == "batch" else 100)
+    mcmc = measure_mcmc(b, wl, staged, n_mcmc)
+
+    # literal reference callable: MonoOnlyLogProb(params[W, 6], lc_array, priors_dict, model) -- pays the
+    # content check of the light-curve array on every call
+    e2e_callable = None
+    if wl["C"] == 1:
+        model = nb.MonotransitModel(*wl["theta"])
+        model.oversamp = wl["S"]
+        pri_d = _priors_dict(wl["priors"])
+        call = lambda: nb.MonoOnlyLogProb(wl["pos"], wl["lc"], pri_d, model, mode="brute")
+        b.host_loop(call, warmup)
+        dt, got = b.host_loop(call, steps)
+        assert np.allclose(got, head["ref_out"][0], rtol=1e-12, atol=0, equal_nan=True)
+        e2e_callable = {"value": wl["W"] * wl["N"] * world / (dt / steps), "unit": "wt/s", "ms_per_step": 1e3 * dt / steps,
+                        "note": "nb.MonoOnlyLogProb(params[W,6], lc ndarray, priors dict, model), brute force: the staged "
+                                "light curve is found by address + full-content checksum on every call"}
+
+    extra = {}
+    if not args.profile:
+        extra["walker_split"] = measure_split(b)
+    if world == 1 and not args.profile and args.workload == "auto":
+        # the other BASELINE configurations on this GPU, as extra keys
+        wl2 = make_workload("k2")
+        st2 = stage(nb, wl2)
+        r2 = measure_lnprob(b, wl2, st2, steps, warmup, variants=False)
+        m2 = measure_mcmc(b, wl2, st2, 200)
+        extra["config2"] = {"workload": WORKLOAD_DESC["k2"], "brute": r2["brute"], "windowed": r2["windowed"],
+                            "e2e_brute": r2["e2e_brute"], "e2e_windowed": r2["e2e_windowed"], "mcmc": m2,
+                            "kernels": list(r2["kernels"]), "stage_ms": list(r2["stage_ms"])}
+        # GP noise-model objective (the reference's default, MonoLogProb) on config 2: reported separately
+        extra["gp"] = measure_gp(b, wl2, st2, steps)
+        st2.close()
+        c1, wl1 = measure_config1(b)
+        extra["config1"] = c1
+        wlb = make_batch(0)
+        stb = stage(nb, wlb)
+        rb = measure_lnprob(b, wlb, stb, steps, warmup, variants=False)
+        mb = measure_mcmc(b, wlb, stb, 50, modes=("windowed",))
+        extra["candidate_batch"] = {"workload": WORKLOAD_DESC["batch"], "candidates": wlb["C"], "brute": rb["brute"],
+                                    "windowed": rb["windowed"], "e2e_brute": rb["e2e_brute"],
+                                    "e2e_windowed": rb["e2e_windowed"], "mcmc_windowed": mb["windowed"],
+                                    "kernels": list(rb["kernels"]), "stage_ms": list(rb["stage_ms"]),
+                                    "note": "one GPU's share of BASELINE configs[3]; the headline of the N > 1 lines"}
+        stb.close()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    units = W * N * world
-    value = units / (ms_brute / args.steps * 1e-3)
-    flops, fl_sweep, fl_eval, (m, m_int, m_edge, t_in) = algorithmic_flops(wl)
     peak_tf, _ = nb.measure_fp64_peak()
-    step_s = ms_brute / args.steps * 1e-3
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload) or {}
+            traffic = json.load(open(tpath)).get(name) or {}
         except Exception:
             traffic = {}
-    kernels = []
-    for name, ms, fl in ((k_s1, ms_s1, fl_sweep), (k_s2, ms_s2, fl_eval)):
-        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        kernels.append({"kernel": name, "ms_per_launch": ms,
-                        "share_of_step": ms / (ms_s1 + ms_s2) if ms_s1 + ms_s2 > 0 else None,
-                        "flops_per_launch": fl, "achieved": tf, "frac": tf / peak_tf, "traffic": traffic.get(name)})
-    dom = max(kernels, key=lambda k: k["ms_per_launch"])
+    cfg = workload_config(name, wl, args.gpus)
+    cfg.update({
+        "arithmetic": "NMB_F64: FP64 with contracted multiply-adds and <= 1.5-ulp quotients / roots in the two "
+                      "hot occultation cases (lnprob within 1e-13 of the reference, tolerance 1e-10); the "
+                      "reference's own rounding sequence is timed under 'strict'",
+        "l2": "192 MiB buffer zeroed between timed iterations",
+        "n1_same_workload_key": "candidate_batch" if name == "batch" else None})
     line = {
-        "metric": "lnprob_walker_timestamp_evals_per_sec", "value": value, "unit": "wt/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_brute / args.steps,
+        "metric": METRIC, "value": head["brute"]["value"], "unit": "wt/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": head["brute"]["ms_per_step"],
+        "ms_per_step_median": head["brute"]["ms_per_step_median"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC[args.workload], "N": N, "S": S, "W": W,
-                   "step": "one full-ensemble lnprob evaluation (likelihood + priors), brute-force kernel",
-                   "arithmetic": "NMB_F64: FP64 with contracted multiply-adds and <= 1.5-ulp quotients / roots in the two "
-                                 "hot occultation cases (lnprob within 1e-13 of the reference, tolerance 1e-10); the "
-                                 "reference's own rounding sequence is timed under 'strict'",
-                   "parallelism": "independent candidate per GPU, no collective" if world > 1 else "single GPU",
-                   "l2": "192 MiB buffer zeroed between timed iterations (inputs are 0.15 MB, L2/SMEM resident by design)"},
-        "clocks": clk,
-        "e2e": {"value": units / (dt_e2e / args.steps), "unit": "wt/s",
-                "h2d_bytes_per_step": int(W * 6 * 8 + 36 * 8), "d2h_bytes_per_step": int(W * 8),
-                "ms_per_step": 1e3 * dt_e2e / args.steps,
-                "note": "LightCurve.lnprob(numpy params) -> numpy lnprob; light curve staged once like emcee args="},
-        "gpu_launches": int(launches),
-        "mcmc": {"steps": n_mcmc, "walkers_per_gpu": W, "windowed": mcmc["windowed"], "brute": mcmc["brute"],
-                 "note": "one step = every walker proposed once (two half-ensemble phases); chain kept in HBM"},
-        "windowed": {"value": units / (ms_win / args.steps * 1e-3), "unit": "wt/s",
-                     "ms_per_step": ms_win / args.steps, "speedup_vs_brute": ms_brute / ms_win,
-                     "e2e": units / (dt_e2e_win / args.steps),
-                     "note": "exact prefix-sum + in-transit-window kernel; effective wt/s, not a roofline figure"},
-        "fp32": {"value": units / (ms_f32 / args.steps * 1e-3), "unit": "wt/s", "ms_per_step": ms_f32 / args.steps,
-                 "max_rel_err_vs_fp64": f32_err,
-                 "note": "NMB_F32: FP32 transit model (depth space) in the windowed pipeline; reported separately"},
-        "strict": {"value": W * N * world * args.steps / (ms_strict * 1e-3), "unit": "wt/s", "ms_per_step": ms_strict / args.steps,
-                   "max_rel_diff_default_vs_strict": strict_diff,
-                   "note": "NMB_F64_STRICT, brute force: the hot occultation cases in the reference's own rounding sequence "
-                           "(bit-identical to NumPy in most elements); the default NMB_F64 contracts multiply-adds and uses "
-                           "<= 1.5-ulp quotients / roots there (lnprob within 1e-13 of the reference, tolerance 1e-10)"},
-        "walker_split": split,
-        "gp": {"value": units / (ms_gp * 1e-3), "unit": "wt/s", "ms_per_step": ms_gp, "ndim": 8,
-               "note": "MonoLogProb: celerite RealTerm + jitter with the transit model as mean (2 free kernel "
-                       "parameters + 6 transit parameters); sequential O(N) solve per walker, reported separately"},
-        "roofline": {"bound": "fp64", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": dom["frac"], "traffic": dom["traffic"],
-                     "peak_source": "DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 entry)",
-                     "flops_convention": "SURVEY.md 8(d): 7/fine sample + 143 interior + 180 ingress + 5/timestamp + 40/walker",
-                     "fine_samples": m, "interior": m_int, "edge": m_edge, "in_transit_timestamps": t_in,
-                     "kernels": kernels,
-                     "whole_step": {"flops": flops, "ms": ms_brute / args.steps, "achieved": flops / step_s / 1e12,
-                                    "frac": flops / step_s / 1e12 / peak_tf},
-                     "note": "dominant kernel = the longer of the two launches of a brute-force step; per-kernel "
-                             "durations from CUDA events between the kernels (they do not overlap while measured)"},
+        "config": cfg,
+        "clocks": head.get("clocks"),
+        "e2e": {"value": head["e2e_brute"]["value"], "unit": "wt/s",
+                "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
+                "ms_per_step": head["e2e_brute"]["ms_per_step"],
+                "note": "LightCurve.lnprob(numpy params, priors) -> numpy lnprob, brute force like `value`; light curve "
+                        "staged once like emcee args="},
+        "e2e_callable": e2e_callable,
+        "gpu_launches": int(head["launches"]),
+        "mcmc": mcmc,
+        "windowed": dict(head["windowed"], e2e=head["e2e_windowed"]["value"]),
+        "fp32": head.get("fp32"), "strict": head.get("strict"),
+        "roofline": roofline_of(b, wl, head, peak_tf, traffic),
+        "parity": {"likelihood": "pinned (oracle bitwise vs the reference's own NumPy code; 3 logged known answers)",
+                   "sampler": "unpinned (emcee absent: stretch move restated from the publication)",
+                   "gp": "unpinned (celerite absent: recurrence restated from the publication)"},
     }
+    line.update(extra)
     if world == 1 and not args.no_cpu and not args.profile:
-        import multiprocessing as mp
-        cores = len(os.sched_getaffinity(0))
-        pool = mp.Pool(cores)
-        rate, nwalk, dt = cpu_reference_rate(wl, 24.0, pool, cores)  # lands at 10-15 s of CPU work
-        pool.close()
-        line["cpu_baseline"] = {"value": rate, "unit": "wt/s", "cores": cores, "kind": "port",
-                                "sample": "%d walker evaluations of the same workload (N=%d, S=%d) in %.1f s, "
-                                          "NumPy oracle in a %d-process pool" % (nwalk, N, S, dt, cores)}
+        line["cpu_baseline"] = cpu_baseline(wl)
+        if "config1" in extra:
+            extra["config1"]["cpu_mcmc"] = cpu_config1_mcmc(wl1)
+            extra["config1"]["cpu_baseline"] = cpu_baseline(wl1, budget_s=6.0)
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_gp(b, wl, staged, steps):
+    import ctypes
+    torch = b.torch
+    from namaste_b200._lib import load as _load, check as _check, ptr as _ptr
+    W = wl["W"]
+    kfix = np.array([np.log(np.var(wl["lc"][:, 1])), -np.log(3.0), np.log(np.median(wl["lc"][:, 2]))])
+    gp_pos = np.hstack([kfix[None, :2] + 0.1 * np.random.default_rng(3 + b.rank).standard_normal((W, 2)), wl["pos"]])
+    d_gp = torch.from_numpy(np.ascontiguousarray(gp_pos)).cuda()
+    gp_out = torch.empty((1, W), dtype=torch.float64, device="cuda")
+
+    def call():
+        _check(_load().nmb_gp_lnprob(staged._h, _ptr(d_gp), W, 0, _ptr(kfix), 3, None, _ptr(gp_out), None,
+                                     ctypes.c_void_p(b.stream.cuda_stream)), "gp")
+    gp_steps = max(3, min(steps, 20))
+    b.device_loop(call, 3)
+    ms, _, _ = b.device_loop(call, gp_steps)
+    return {"value": W * wl["N"] / (float(ms.mean()) * 1e-3), "unit": "wt/s", "ms_per_step": float(ms.mean()), "ndim": 8,
+            "workload": WORKLOAD_DESC["k2"],
+            "note": "MonoLogProb: celerite RealTerm + jitter with the transit model as mean (2 free kernel "
+                    "parameters + 6 transit parameters); sequential O(N) solve per walker, reported separately"}
 
 
 def _emit(line):
@@ -519,13 +780,13 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="k2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto", "batch"] + sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true",
-                    help="short run for ncu: no clock-sampling continuation, no cpu_baseline")
+                    help="short run for ncu: headline legs only, no clock-sampling continuation, no cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -130,6 +130,24 @@ int nmb_sampler_halfstep(nmb_sampler* s, int half, int64_t k0, int64_t nk, int s
 /* ... then close the step (RNG counter, chain column; append_all appends the whole ensemble) */
 int nmb_sampler_advance(nmb_sampler* s, int stored, int append_all);
 int nmb_sampler_sync(nmb_sampler* s);
+/* ---- one ensemble split by walker over several GPUs of a node, one process per GPU (BASELINE config 5).
+ * The reference has no counterpart (its parallelism is emcee's process pool, namaste/namaste.py:583/590); the
+ * half-ensemble dependency of the stretch move it drives (:590-594) is what the exchange preserves.
+ * Every rank creates the same sampler (same W, priors, seed) and sets the same state; then
+ *   export : 64-byte CUDA IPC handle of this rank's ensemble replica (pos, lnp, arrival flags)
+ *   attach : handles [world][64] of all ranks in rank order (the own entry is ignored); maps the peers
+ *   run_split : nsteps steps; per half-step the rank updates walkers [rank*nk, (rank+1)*nk), nk = W/2/world,
+ *               of the active half, stores them into every peer's replica over NVLink and exchanges arrival
+ *               flags -- device side, no NCCL, no host round trip; store_all appends the whole ensemble to
+ *               this rank's chain every step.  The chain has the bits of the single-GPU chain of that seed.
+ * world = 1 needs no attach.  pack_half / unpack_half are the building blocks of the NCCL transport of the
+ * same exchange (one all-gather of [nk][ndim + 1] rows per half-step): device buffers, sampler's stream. */
+#define NMB_IPC_HANDLE_BYTES 64
+int nmb_sampler_split_export(nmb_sampler* s, void* handle_out /*64 bytes*/);
+int nmb_sampler_split_attach(nmb_sampler* s, int rank, int world, const void* handles /*[world][64]*/);
+int nmb_sampler_run_split(nmb_sampler* s, int64_t nsteps, int store_all);
+int nmb_sampler_pack_half(nmb_sampler* s, int half, int64_t k0, int64_t nk, double* out /*[nk][ndim+1]*/);
+int nmb_sampler_unpack_half(nmb_sampler* s, int half, const double* in /*[W/2][ndim+1]*/);
 int nmb_sampler_reset(nmb_sampler* s);
 int64_t nmb_sampler_len(const nmb_sampler* s);   /* stored chain columns */
 int64_t nmb_sampler_steps(const nmb_sampler* s); /* steps taken (RNG counter) */
@@ -176,6 +194,11 @@ int nmb_stage_times(nmb_lc* lc, double* stage1_ms, double* stage2_ms, int64_t* c
 int nmb_last_kernels(nmb_lc* lc, const char** stage1, const char** stage2);
 /* diagnostics: phase envelopes (globaltimer ns) of the last evaluation; needs NMB_TRACE=1 in the environment */
 int nmb_debug_trace(nmb_lc* lc, uint64_t* out16);
+/* host utility: position-sensitive 128-bit checksum of `nwords` 64-bit words of a host array (one pass at memory
+ * speed).  The Python layer keys its cache of staged light curves on it, so that the reference's call
+ * MonoOnlyLogProb(params, lc, priors, model) with the same `lc` array (namaste/namaste.py:590, emcee args=) finds
+ * the device copy again and notices in-place edits. */
+int nmb_host_checksum(const void* data, int64_t nwords, uint64_t* out2);
 /* number of kernels this library has launched so far in this process */
 int64_t nmb_launch_count(void);
 

@@ -51,6 +51,11 @@ SIGNATURES = {
     "nmb_sampler_halfstep": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     "nmb_sampler_advance": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     "nmb_sampler_sync": (ctypes.c_int, [_vp]),
+    "nmb_sampler_split_export": (ctypes.c_int, [_vp, _vp]),
+    "nmb_sampler_split_attach": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "nmb_sampler_run_split": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int]),
+    "nmb_sampler_pack_half": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp]),
+    "nmb_sampler_unpack_half": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "nmb_sampler_reset": (ctypes.c_int, [_vp]),
     "nmb_sampler_len": (ctypes.c_int64, [_vp]),
     "nmb_sampler_steps": (ctypes.c_int64, [_vp]),
@@ -66,6 +71,7 @@ SIGNATURES = {
     "nmb_last_kernels": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p)]),
     "nmb_stage_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "nmb_stage_times": (ctypes.c_int, [_vp, _c_double_p, _c_double_p, ctypes.POINTER(ctypes.c_int64)]),
+    "nmb_host_checksum": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
     "nmb_launch_count": (ctypes.c_int64, []),
 }
 

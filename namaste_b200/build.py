@@ -8,8 +8,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnamaste_b200.so")
-SOURCES = ["api.cu"]
-HEADERS = ["transit_math.cuh", "lnprob_kernels.cuh", "eval_pipeline.cuh", "sampler.cuh", "gp_kernels.cuh", "flatten_kernels.cuh", "summary_kernels.cuh", os.path.join("..", "..", "include", "namaste_b200.h")]
+# api.cu holds the C-ABI entry points; inst_s*.cu instantiate the pipeline for one supersampling factor each
+# (see csrc/api_internal.cuh), so the translation units compile in parallel
+SOURCES = ["api.cu", "inst_s0.cu", "inst_s1.cu", "inst_s10.cu", "inst_s11.cu", "inst_s15.cu"]
+HEADERS = ["api_internal.cuh", "transit_math.cuh", "lnprob_kernels.cuh", "eval_pipeline.cuh", "sampler.cuh", "gp_kernels.cuh",
+           "flatten_kernels.cuh", "summary_kernels.cuh", "split_kernels.cuh",
+           os.path.join("..", "..", "include", "namaste_b200.h")]
+OBJDIR = os.path.join(HERE, "build")
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -17,7 +22,7 @@ NVCC_FLAGS = [
     # the transit arithmetic mirrors the reference operation by operation; FMAs are
     # written explicitly (fma()) only where a single rounding is provably harmless
     "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -40,13 +45,28 @@ def build_library(force=False, verbose=False):
     """Compile csrc/*.cu -> namaste_b200/libnamaste_b200.so (skipped when up to date)."""
     if not force and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+        if verbose:
+            sys.stderr.write(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    tmp = LIB + ".tmp"
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -1,121 +1,13 @@
 // C-ABI entry points (include/namaste_b200.h): light-curve staging, launches, error plumbing.
-#include <algorithm>
-#include <atomic>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <utility>
-#include <vector>
-
-#include "../../include/namaste_b200.h"
-#include "eval_pipeline.cuh"
+#include "api_internal.cuh"
+// kernels only the entry points launch (not templates on S): defined in this translation unit alone
 #include "gp_kernels.cuh"
 #include "flatten_kernels.cuh"
 #include "summary_kernels.cuh"
-
-namespace {
+#include "split_kernels.cuh"
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-
-int fail(int code, const std::string& msg) {
-    g_err = msg;
-    return code;
-}
-int cuda_fail(cudaError_t e, const char* what) {
-    return fail(NMB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-}
-#define CU(call)                                                   \
-    do {                                                           \
-        cudaError_t e__ = (call);                                  \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
-    } while (0)
-
-constexpr int kThreads = 128;  // sweep / window block size
-constexpr int kTPT = 4;        // timestamps per thread in the sweep -> 512-timestamp tiles
-constexpr int kTile = kThreads * kTPT;
-constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-thread sweep
-
-}  // namespace
-
-// Per-stage device timing (nmb_stage_timing / nmb_stage_times): CUDA events around stage 1 and
-// stage 2 of every evaluation on the launching stream.  The event between the two kernels keeps
-// them from overlapping, so these are per-kernel durations, not a decomposition of the step time.
-struct StageTimer {
-    bool on = false;
-    static constexpr int kRing = 64;
-    cudaEvent_t e[kRing][3] = {};
-    int head = 0, pending = 0;
-    double acc1 = 0, acc2 = 0;
-    long n = 0;
-    void enable(bool v) {
-        if (v && !e[0][0])
-            for (auto& r : e) for (auto& x : r) cudaEventCreate(&x);
-        on = v;
-    }
-    void mark(int i, cudaStream_t st) { if (on) cudaEventRecord(e[head][i], st); }
-    void drain(int keep) {
-        while (pending > keep) {
-            const int idx = (head - pending + 2 * kRing) % kRing;
-            cudaEventSynchronize(e[idx][2]);
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, e[idx][0], e[idx][1]);
-            cudaEventElapsedTime(&b, e[idx][1], e[idx][2]);
-            acc1 += a; acc2 += b; ++n;
-            --pending;
-        }
-    }
-    void done() {
-        if (!on) return;
-        head = (head + 1) % kRing;
-        ++pending;
-        drain(kRing - 1);
-    }
-    ~StageTimer() {
-        if (e[0][0]) for (auto& r : e) for (auto& x : r) cudaEventDestroy(x);
-    }
-};
-
-struct nmb_lc {
-    const char* last_stage1 = "";  // kernels of the last nmb_lnprob evaluation (nmb_last_kernels)
-    const char* last_stage2 = "";
-    int64_t ncand = 0, nmax = 0, npad = 0;
-    int S = 0;
-    int gran = 64, ngran = 0;
-    int device = 0;
-    std::vector<int64_t> n;
-    std::vector<double> cad;
-    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_term = nullptr, *d_var = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
-    long long* d_n = nullptr;
-    int *d_tgrid = nullptr, *d_gcount = nullptr;
-    double *d_t0 = nullptr, *d_ginv = nullptr;
-    int64_t gstride = 0;
-    // reduction workspace of the fused kernel (grown on demand)
-    double* d_partials = nullptr;
-    int* d_tickets = nullptr;
-    size_t partials_cap = 0, tickets_cap = 0;
-    // workspace of the two-stage pipeline (grown on demand)
-    nmb::EvalWs ws{};
-    size_t ws_cw = 0, ws_partials = 0;
-    // staging for the host-buffer entry point
-    double *h_pin = nullptr, *d_stage = nullptr;
-    size_t pin_cap = 0, stage_cap = 0;
-    cudaStream_t own_stream = nullptr;
-    StageTimer timer;
-    // GP objective: binned in-transit model [CW][npad] and the repacked transit parameters [CW][6]
-    double *d_modelbuf = nullptr, *d_meanpar = nullptr;
-    size_t modelbuf_cap = 0, meanpar_cap = 0;
-
-    nmb::LcView view() const {
-        nmb::LcView v;
-        v.t = d_t; v.f = d_f; v.w = d_w; v.term = d_term; v.gran = gran; v.ngran = ngran; v.pre_hi = d_pre_hi; v.pre_lo = d_pre_lo; v.off = d_off;
-        v.n = d_n; v.npad = npad; v.ncand = (int)ncand; v.S = S;
-        v.tgrid = d_tgrid; v.t0 = d_t0; v.ginv = d_ginv; v.gcount = d_gcount; v.gstride = gstride;
-        return v;
-    }
-};
 
 extern "C" const char* nmb_last_error(void) { return g_err.c_str(); }
 extern "C" const char* nmb_version(void) { return "namaste_b200 0.1 (sm_100a)"; }
@@ -131,6 +23,7 @@ extern "C" void nmb_lc_destroy(nmb_lc* lc) {
     cudaFree(lc->ws.grouptick); cudaFree(lc->ws.counters); cudaFree(lc->ws.trace);
     if (lc->h_pin) cudaFreeHost(lc->h_pin);
     if (lc->own_stream) cudaStreamDestroy(lc->own_stream);
+    if (lc->ws_event) cudaEventDestroy(lc->ws_event);
     delete lc;
 }
 
@@ -290,374 +183,6 @@ extern "C" int64_t nmb_lc_npoints(const nmb_lc* lc, int64_t c) { return (lc && c
 extern "C" double nmb_lc_cadence(const nmb_lc* lc, int64_t c) { return (lc && c >= 0 && c < lc->ncand) ? lc->cad[c] : NAN; }
 extern "C" int nmb_lc_oversamp(const nmb_lc* lc) { return lc ? lc->S : 0; }
 
-namespace {
-
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return NMB_OK;
-}
-
-constexpr int kEvalThreads = 128;
-
-// Launch with programmatic dependent launch enabled (see pdl_wait / pdl_trigger): the kernel may be
-// scheduled while its predecessor in the stream drains.  NMB_NO_PDL=1 restores plain launches.
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    static const bool off = std::getenv("NMB_NO_PDL") != nullptr;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = off ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
-}
-
-
-
-int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
-    nmb::EvalWs& ws = lc->ws;
-    if (CW > lc->ws_cw) {
-        cudaFree(ws.oot); cudaFree(ws.wcs); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.nslots);
-        cudaFree(ws.slots); cudaFree(ws.slotpart); cudaFree(ws.slotsdone); cudaFree(ws.grouptick);
-        cudaFree(ws.counters); cudaFree(ws.trace);
-        cudaFree(ws.partials);
-        ws = nmb::EvalWs{};
-        lc->ws_cw = 0; lc->ws_partials = 0;
-        // timestamps per pass: as many whole bins as fit in kEvalPass supersamples; slots per walker:
-        // one pass each up to a pool of 4 M slots over the ensemble (>= 64 per walker)
-        ws.tsw = std::max(1, nmb::kEvalPass / lc->S);
-        // slots a warp evaluates in one pass: ~270 supersamples, two slots when the bins are long
-        // (measured: S = 15 prefers 2, S = 10 / 11 prefer 3-4; differences of a few per cent)
-        ws.merge = lc->S >= 13 ? 2 : 3;
-        if (const char* m = std::getenv("NMB_EVAL_MERGE")) ws.merge = std::max(1, std::min(nmb::kEvalMerge, std::atoi(m)));
-        const size_t full = (size_t)(lc->npad + ws.tsw - 1) / ws.tsw;
-        ws.maxslots = (int)std::min<size_t>(full, std::max<size_t>(64, (size_t)4194304 / CW));
-        const size_t cap = CW * ws.maxslots;
-        CU(cudaMalloc(&ws.oot, CW * sizeof(double)));
-        CU(cudaMalloc(&ws.wcs, CW * sizeof(nmb::WalkerConsts)));
-        CU(cudaMalloc(&ws.rlo, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.rhi, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.slotsdone, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.nslots, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.slots, cap * sizeof(nmb::SlotRec)));
-        CU(cudaMalloc(&ws.slotpart, cap * sizeof(double)));
-        CU(cudaMalloc(&ws.grouptick, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.counters, 4 * sizeof(int)));
-        if (std::getenv("NMB_TRACE")) {
-            CU(cudaMalloc(&ws.trace, 16 * sizeof(unsigned long long)));
-            CU(cudaMemsetAsync(ws.trace, 0, 16 * sizeof(unsigned long long), st));
-        }
-        CU(cudaMemsetAsync(ws.grouptick, 0, CW * sizeof(int), st));
-        CU(cudaMemsetAsync(ws.counters, 0, 4 * sizeof(int), st));
-        nmb::init_ranges_kernel<<<(unsigned)((CW + 255) / 256), 256, 0, st>>>(ws.rlo, ws.rhi, ws.slotsdone, (int)CW);
-        g_launches++;
-        CU(cudaGetLastError());
-        lc->ws_cw = CW;
-    }
-    if (CW * ntiles > lc->ws_partials) {
-        cudaFree(ws.partials);
-        ws.partials = nullptr; lc->ws_partials = 0;
-        CU(cudaMalloc(&ws.partials, CW * ntiles * sizeof(double)));
-        lc->ws_partials = CW * ntiles;
-    }
-    return NMB_OK;
-}
-
-// blocks per SM of the next eval_slots launch (0: one resident wave).  Behind window_direct_kernel the queue only
-// holds the few long-range walkers, often nothing: a small grid is cheaper to start and to drain.
-static thread_local int g_eval_blocks_per_sm = 0;
-
-template <int S, int MINB, int PATH>
-int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                   cudaStream_t st, const nmb::SampleCtx& sc) {
-    auto kern = nmb::eval_slots_kernel<S, kEvalThreads, MINB, PATH>;
-    const size_t smem = sizeof(nmb::EvalSmem<kEvalThreads>);
-    static thread_local int per_sm = 0, sms = 0;
-    if (!per_sm) {
-        if (int rc = set_smem(kern, smem)) return rc;
-        int dev = 0;
-        CU(cudaGetDevice(&dev));
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEvalThreads, smem));
-        per_sm = std::max(per_sm, 1);
-    }
-    const int bps = g_eval_blocks_per_sm > 0 ? std::min(g_eval_blocks_per_sm, per_sm) : per_sm;
-    const int grid = sms * bps;  // one resident wave, or a part of it
-    CU(launch_pdl(kern, dim3(grid), dim3(kEvalThreads), smem, st, lc->view(), params, W, priors, lc->ws, sms, lnprob,
-                  loglike, sc));
-    g_launches++;
-    return NMB_OK;
-}
-
-template <int S>
-int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
-    if (dtype == NMB_F32) return launch_eval_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
-    if (dtype == NMB_F64_STRICT) return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
-    // relaxed path: five blocks (20 warps) per SM.  It fits 96 registers with two spilled words, and the shorter
-    // per-warp share of the queue outweighs them (measured: -4 % ... -7 % on every workload against four
-    // blocks; six blocks spill inside the flux rounds and lose)
-    return launch_eval_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
-}
-
-// Stage 2 as one launch of queue workers + one direct block per walker (eval_mixed_kernel).
-template <int S, int MINB, int PATH>
-int launch_mixed_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                    cudaStream_t st, const nmb::SampleCtx& sc) {
-    auto kern = nmb::eval_mixed_kernel<S, kEvalThreads, MINB, PATH>;
-    const size_t smem = std::max(sizeof(nmb::EvalSmem<kEvalThreads>), sizeof(nmb::DirectSmem<kEvalThreads>));
-    static thread_local int sms = 0, per_sm = 0;
-    if (!sms) {
-        if (int rc = set_smem(kern, smem)) return rc;
-        int dev = 0;
-        CU(cudaGetDevice(&dev));
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEvalThreads, smem));
-        per_sm = std::max(per_sm, 1);
-    }
-    // queue workers: one resident wave, like eval_slots_kernel (those that find the queue empty exit at once)
-    static const int nq_force = std::getenv("NMB_MIXED_NQ") ? std::max(1, std::atoi(std::getenv("NMB_MIXED_NQ"))) : 0;
-    const int nq = sms * (nq_force ? nq_force : per_sm);
-    const size_t CW = (size_t)lc->ncand * W;
-    CU(launch_pdl(kern, dim3((unsigned)(nq + CW)), dim3(kEvalThreads), smem, st, lc->view(), params, W, priors, lc->ws, sms,
-                  nq, lnprob, loglike, sc));
-    g_launches++;
-    return NMB_OK;
-}
-
-template <int S>
-int launch_mixed(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
-    if (dtype == NMB_F32) return launch_mixed_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
-    if (dtype == NMB_F64_STRICT) return launch_mixed_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
-    return launch_mixed_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
-}
-
-// Ensembles between a few hundred walkers and about two resident waves of direct blocks take the mixed
-// stage 2: short ranges are evaluated by a block per walker, only long ranges are queued.  Below that the
-// queue alone already gives every slot its own warp (config 1, 100 walkers: 30.7 us against 34.7 us mixed);
-// above it the queue balances better than waves of blocks.  Measured on config 2 (1024 walkers) against the
-// queue alone: repeated evaluations on a warm L2 (the sampler, host-API calls) gain -- MCMC 12.8 k -> 14.0 k
-// steps/s brute force, e2e 5.4e10 -> 5.8e10 wt/s, windowed step 46.0 -> 44.2 us -- while a brute-force step
-// on a flushed L2 loses 2.6 us (49.9 -> 52.5 us: three waves of direct blocks, each paying its cold misses).
-// NMB_MIXED_MINCW / NMB_MIXED_MAXCW override.
-static bool use_mixed(const nmb_lc* lc, size_t CW) {
-    static const long long lo = std::getenv("NMB_MIXED_MINCW") ? std::atoll(std::getenv("NMB_MIXED_MINCW")) : 256;
-    static const long long hi = std::getenv("NMB_MIXED_MAXCW") ? std::atoll(std::getenv("NMB_MIXED_MAXCW")) : 1184;
-    return !lc->ws.modelbuf && (long long)CW >= lo && (long long)CW <= hi;
-}
-
-// Slots a direct block of eval_mixed_kernel takes: two per warp (six flux rounds).  A longer range in one
-// block makes it the straggler of the launch while queue workers run beside it and could spread that
-// walker over the whole GPU (config 1 with the mixed path forced: 40.4 us with three slots per warp, 34.7 us
-// with two).  window_direct_kernel takes one full pass per warp (`merge` slots): there the queue only
-// starts after the direct blocks, so fewer queued walkers is the better trade.
-static int direct_cap_slots(const nmb_lc* lc, bool queue_runs_beside) {
-    static const int per_warp = std::getenv("NMB_DIRECT_SLOTS") ? std::max(1, std::atoi(std::getenv("NMB_DIRECT_SLOTS"))) : 2;
-    return (kEvalThreads / 32) * (queue_runs_beside ? std::min(per_warp, lc->ws.merge) : lc->ws.merge);
-}
-
-template <int S, int THREADS, int MINB>
-int launch_sweep_t(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                   cudaStream_t st, const nmb::SampleCtx& sc) {
-    auto kern = nmb::sweep_walkers_kernel<S, THREADS, kSweepChunk, MINB>;
-    const size_t smem = sizeof(nmb::WalkSmem<S, kSweepChunk>);
-    static thread_local int resident = 0;
-    if (!resident) {
-        if (int rc = set_smem(kern, smem)) return rc;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        int dev = 0, sms = 0, per_sm = 0;
-        CU(cudaGetDevice(&dev));
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-        resident = sms * std::max(per_sm, 1);
-    }
-    const size_t CW = (size_t)lc->ncand * W;
-    (void)CW;
-    const int nwb = (W + THREADS - 1) / THREADS;
-    // granules per block: many more blocks than resident slots, so that the hardware block scheduler
-    // evens out the SMs (measured: 5-8 % faster than one exactly-resident wave on the 65 k and 500 k
-    // light curves), but at least ~256 timestamps per block to amortise its prologue
-    static const int force_gpb = std::getenv("NMB_GPB") ? std::atoi(std::getenv("NMB_GPB")) : 0;
-    const long long units = (long long)lc->ncand * nwb * lc->ngran;
-    const long long by_balance = std::max<long long>(1, units / (4LL * resident));
-    const long long by_work = std::max<long long>(1, (256 + lc->gran - 1) / lc->gran);
-    int gpb = (int)std::min(by_balance, by_work);
-    if (force_gpb > 0) gpb = force_gpb;
-    gpb = std::min(gpb, lc->ngran);
-    const int ntb = (lc->ngran + gpb - 1) / gpb;
-    dim3 grid(ntb, nwb, (unsigned)lc->ncand);
-    CU(launch_pdl(kern, grid, dim3(THREADS), smem, st, lc->view(), params, W, gpb, priors, lc->ws, lnprob, loglike, sc));
-    g_launches++;
-    return NMB_OK;
-}
-
-template <int S>
-int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
-    const size_t CW = (size_t)lc->ncand * W;
-    if (int rc = ensure_ws(lc, CW, lc->ngran, st)) return rc;
-    const bool mixed = use_mixed(lc, CW);
-    lc->ws.direct_cap = mixed ? direct_cap_slots(lc, true) : 0;
-    lc->timer.mark(0, st);
-    // 128-walker blocks when they alone fill the GPU, single-warp blocks (finer spread) otherwise
-    static const int force_thr = std::getenv("NMB_SWEEP_THREADS") ? std::atoi(std::getenv("NMB_SWEEP_THREADS")) : 0;
-    const long long blocks128 = (long long)lc->ncand * ((W + 127) / 128) * lc->ngran;
-    const bool wide = force_thr ? (force_thr == 128) : (W >= 128 || blocks128 >= 4 * 148);
-    int rc = !wide ? launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc)
-                   : launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc);
-    if (rc) return rc;
-    lc->timer.mark(1, st);
-    rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
-               : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
-    lc->last_stage1 = "sweep_walkers_kernel";
-    lc->last_stage2 = mixed ? "eval_mixed_kernel" : "eval_slots_kernel";
-    lc->timer.mark(2, st);
-    lc->timer.done();
-    return rc;
-}
-
-template <int S, int PATH, int THREADS>
-int launch_direct_t(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                    cudaStream_t st, const nmb::SampleCtx& sc, int* resident_out) {
-    auto kern = nmb::window_direct_kernel<S, THREADS, 512 / THREADS, PATH>;
-    const size_t smem = sizeof(nmb::DirectSmem<THREADS>);
-    static thread_local int resident = 0;
-    if (!resident) {
-        if (int rc = set_smem(kern, smem)) return rc;
-        int dev = 0, sms = 0, per_sm = 0;
-        CU(cudaGetDevice(&dev));
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-        resident = sms * std::max(per_sm, 1);
-    }
-    if (resident_out) { *resident_out = resident; if (!params && !sc.enabled) return NMB_OK; }
-    const size_t CW = (size_t)lc->ncand * W;
-    CU(launch_pdl(kern, dim3((unsigned)CW), dim3(THREADS), smem, st, lc->view(), params, W, priors, lc->ws, lnprob,
-                  loglike, sc));
-    g_launches++;
-    return NMB_OK;
-}
-
-// A block of four warps per walker (one slot per warp for a K2 transit).  Used while the ensemble fits one
-// resident wave of such blocks: beyond that the walkers left to the queue would wait for several waves of
-// direct blocks, and the two-kernel pipeline balances better (measured: 1024 walkers of BASELINE config 2,
-// 58 us direct against 50 us through the queue; 512-walker half-steps 24 us against 34 us).
-// *use = false tells the caller to take the queue path.
-template <int S, int PATH>
-int launch_direct(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                  cudaStream_t st, const nmb::SampleCtx& sc, bool* use) {
-    static const int force = std::getenv("NMB_DIRECT") ? std::atoi(std::getenv("NMB_DIRECT")) : -1;
-    static thread_local int resident = 0;
-    if (!resident) {
-        if (int rc = launch_direct_t<S, PATH, 128>(lc, nullptr, W, priors, lnprob, loglike, st, nmb::SampleCtx{}, &resident))
-            return rc;
-    }
-    const size_t CW = (size_t)lc->ncand * W;
-    *use = force >= 0 ? force != 0 : CW <= (size_t)resident;
-    if (!*use) return NMB_OK;
-    return launch_direct_t<S, PATH, 128>(lc, params, W, priors, lnprob, loglike, st, sc, nullptr);
-}
-
-template <int S>
-int launch_window(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
-    const size_t CW = (size_t)lc->ncand * W;
-    if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
-    constexpr int kWinThreads = 64;
-    lc->timer.mark(0, st);
-    // small ensembles: a block per walker evaluates short ranges on the spot (window_direct_kernel); otherwise,
-    // and in the GP model mode, the thread-per-walker kernel fills the queue for eval_slots_kernel
-    bool direct = false;
-    lc->ws.direct_cap = direct_cap_slots(lc, false);  // read by window_direct_kernel only (it never calls push_slots)
-    if (!lc->ws.modelbuf) {
-        int rc = dtype == NMB_F32          ? launch_direct<S, 2>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
-                 : dtype == NMB_F64_STRICT ? launch_direct<S, 1>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
-                                           : launch_direct<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc, &direct);
-        if (rc) return rc;
-    }
-    const bool mixed = !direct && use_mixed(lc, CW);
-    if (!direct) {
-        lc->ws.direct_cap = mixed ? direct_cap_slots(lc, true) : 0;
-        CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),
-                      dim3(kWinThreads), 0, st, lc->view(), params, W, priors, lc->ws, lnprob, loglike, sc));
-        g_launches++;
-    }
-    lc->timer.mark(1, st);
-    // one block per SM behind window_direct_kernel (measured: MCMC +1.3 % on config 2, +3.8 % on config 1)
-    static const int direct_bps = std::getenv("NMB_DIRECT_EVAL_BPS") ? std::atoi(std::getenv("NMB_DIRECT_EVAL_BPS")) : 1;
-    g_eval_blocks_per_sm = direct ? direct_bps : 0;
-    const int rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
-                         : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
-    g_eval_blocks_per_sm = 0;
-    lc->last_stage1 = direct ? "window_direct_kernel" : "window_ranges_kernel";
-    lc->last_stage2 = mixed ? "eval_mixed_kernel" : "eval_slots_kernel";
-    lc->timer.mark(2, st);
-    lc->timer.done();
-    return rc;
-}
-
-template <int S>
-int launch_fused(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
-                 cudaStream_t st) {
-    const int ntiles = (int)(lc->npad / kTile);
-    long long blocks1 = (long long)ntiles * W * lc->ncand;
-    int WT = (int)std::min<long long>(nmb::kWTMax, std::max<long long>(1, blocks1 / (148 * 8)));
-    const int groups = (W + WT - 1) / WT;
-    const size_t need_p = (size_t)lc->ncand * groups * WT * ntiles;
-    const size_t need_t = (size_t)lc->ncand * groups;
-    if (need_p > lc->partials_cap) {
-        cudaFree(lc->d_partials);
-        lc->d_partials = nullptr; lc->partials_cap = 0;
-        CU(cudaMalloc(&lc->d_partials, need_p * sizeof(double)));
-        lc->partials_cap = need_p;
-    }
-    if (need_t > lc->tickets_cap) {
-        cudaFree(lc->d_tickets);
-        lc->d_tickets = nullptr; lc->tickets_cap = 0;
-        CU(cudaMalloc(&lc->d_tickets, need_t * sizeof(int)));
-        CU(cudaMemsetAsync(lc->d_tickets, 0, need_t * sizeof(int), st));
-        lc->tickets_cap = need_t;
-    }
-    auto kern = nmb::lnprob_sweep_kernel<S, kThreads, kTPT, false>;
-    const size_t smem = sizeof(nmb::SweepSmem<S, kThreads, kTPT>);
-    if (int rc = set_smem(kern, smem)) return rc;
-    dim3 grid(ntiles, groups, (unsigned)lc->ncand);
-    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, WT, priors, lc->d_partials, lc->d_tickets, lnprob,
-                                       loglike, nullptr, 0);
-    g_launches++;
-    CU(cudaGetLastError());
-    return NMB_OK;
-}
-
-template <int S>
-int launch_model(nmb_lc* lc, int cand, const double* params, int W, double* model, cudaStream_t st) {
-    const int ntiles = (int)((lc->n[cand] + kTile - 1) / kTile);
-    const int WT = 1;
-    auto kern = nmb::lnprob_sweep_kernel<S, kThreads, kTPT, true>;
-    const size_t smem = sizeof(nmb::SweepSmem<S, kThreads, kTPT>);
-    if (int rc = set_smem(kern, smem)) return rc;
-    dim3 grid(ntiles, W, 1);
-    kern<<<grid, kThreads, smem, st>>>(lc->view(), params, W, WT, nullptr, nullptr, nullptr,
-                                       nullptr, nullptr, model, cand);
-    g_launches++;
-    CU(cudaGetLastError());
-    return NMB_OK;
-}
-
-#define NMB_DISPATCH_S(S_, CALL)                  \
-    switch (S_) {                                 \
-        case 1: { constexpr int SS = 1; CALL; } break;   \
-        case 10: { constexpr int SS = 10; CALL; } break; \
-        case 11: { constexpr int SS = 11; CALL; } break; \
-        case 15: { constexpr int SS = 15; CALL; } break; \
-        default: { constexpr int SS = 0; CALL; } break;  \
-    }
-
-}  // namespace
 
 static int lnprob_impl(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
                        double* loglike, int mode, int dtype, void* stream, const nmb::SampleCtx& sc) {
@@ -667,6 +192,8 @@ static int lnprob_impl(nmb_lc* lc, const double* params, int64_t W, const double
         return fail(NMB_ERR_ARG, "nmb_lnprob: dtype must be NMB_F64, NMB_F64_STRICT or NMB_F32");
     if (dtype == NMB_F32 && mode == NMB_MODE_FUSED) return fail(NMB_ERR_ARG, "nmb_lnprob: NMB_MODE_FUSED is FP64 only");
     cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::recursive_mutex> lock(lc->mu);
+    if (int rc0 = lc->order_on(st)) return rc0;
     int rc = NMB_OK;
     if (mode == NMB_MODE_BRUTE) {
         NMB_DISPATCH_S(lc->S, rc = launch_sweep<SS>(lc, params, (int)W, priors, lnprob, loglike, st, sc, dtype));
@@ -690,6 +217,7 @@ extern "C" int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, cons
                                double* loglike, int mode, int dtype) {
     if (!lc || !params || !lnprob) return fail(NMB_ERR_ARG, "nmb_lnprob_host: null pointer");
     if (W < 1) return fail(NMB_ERR_ARG, "nmb_lnprob_host: W < 1");
+    std::lock_guard<std::recursive_mutex> lock(lc->mu);  // pinned staging and workspace: one caller at a time
     const size_t C = (size_t)lc->ncand;
     const size_t np = C * W * 6, npri = priors ? C * 36 : 0, nout = C * W * (loglike ? 2 : 1);
     const size_t total = np + npri + nout;
@@ -734,6 +262,8 @@ static int gp_lnprob_impl(nmb_lc* lc, const double* params, int64_t W, int kind,
     }
     gs.ndim = gs.nfree + 6;
     cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::recursive_mutex> lock(lc->mu);
+    if (int rc0 = lc->order_on(st)) return rc0;
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, 0, st)) return rc;
     const size_t need = CW * (size_t)lc->npad;
@@ -785,6 +315,7 @@ extern "C" int nmb_gp_lnprob_host(nmb_lc* lc, const double* params, int64_t W, i
                                   int freemask, const double* priors, double* lnprob, double* loglike) {
     if (!lc || !params || !kfixed || !lnprob) return fail(NMB_ERR_ARG, "nmb_gp_lnprob_host: null pointer");
     if (W < 1) return fail(NMB_ERR_ARG, "nmb_gp_lnprob_host: W < 1");
+    std::lock_guard<std::recursive_mutex> lock(lc->mu);
     const int nk = kind == NMB_GP_REAL ? 3 : 5;
     int nfree = 0;
     for (int i = 0; i < nk; ++i) nfree += (freemask >> i) & 1;
@@ -951,6 +482,27 @@ extern "C" int nmb_flatten(const double* t, const double* f, const double* e, in
     return NMB_OK;
 }
 
+// Host utility of the Python layer's staging cache: a position-sensitive checksum of a host array of 64-bit
+// words (sum and sum of prefix sums modulo 2^64, Fletcher style, four interleaved lanes), one pass at memory
+// speed.  It lets the literal reference callable MonoOnlyLogProb(params, lc_array, ...) recognise the light
+// curve it staged before, including in-place edits of a few flux values.
+extern "C" int nmb_host_checksum(const void* data, int64_t nwords, uint64_t* out2) {
+    if ((!data && nwords > 0) || !out2 || nwords < 0) return fail(NMB_ERR_ARG, "nmb_host_checksum: bad argument");
+    const uint64_t* w = static_cast<const uint64_t*>(data);
+    uint64_t s[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
+    int64_t i = 0;
+    for (; i + 4 <= nwords; i += 4) {
+        s[0] += w[i]; t[0] += s[0];
+        s[1] += w[i + 1]; t[1] += s[1];
+        s[2] += w[i + 2]; t[2] += s[2];
+        s[3] += w[i + 3]; t[3] += s[3];
+    }
+    for (int k = 0; i < nwords; ++i, ++k) { s[k] += w[i]; t[k] += s[k]; }
+    out2[0] = s[0] + 3 * s[1] + 5 * s[2] + 7 * s[3];
+    out2[1] = t[0] ^ (t[1] * 0x9E3779B97F4A7C15ull) ^ (t[2] * 0xC2B2AE3D27D4EB4Full) ^ (t[3] * 0x165667B19E3779F9ull);
+    return NMB_OK;
+}
+
 extern "C" int nmb_measure_fp64_peak(double* tflops, double* ms_out) {
     if (!tflops) return fail(NMB_ERR_ARG, "nmb_measure_fp64_peak: null pointer");
     double* d = nullptr;
@@ -1001,6 +553,13 @@ struct nmb_sampler {
     long long step = 0;
     bool has_state = false;
     cudaStream_t st = nullptr;
+    // walker split over several GPUs: pos, lnp and the arrival flags live in ONE allocation (d_xchg) whose
+    // IPC handle the peers open; peer_base[r] is rank r's block mapped into this process (null for self)
+    double* d_xchg = nullptr;
+    int* d_flags = nullptr;    // [kMaxPeers] arrival epochs written by the peers, then [0] ticket, [1] error
+    int split_rank = 0, split_world = 1;
+    void* peer_base[nmb::kMaxPeers] = {};
+    long long split_epoch = 0;
 };
 
 namespace {
@@ -1011,6 +570,11 @@ __global__ void append_chain_kernel(nmb::SampleCtx sc, long long n) {
     double* row = sc.chain + (g * sc.tcap + sc.tcol) * sc.ndim;
     for (int d = 0; d < sc.ndim; ++d) row[d] = sc.pos[g * sc.ndim + d];
     sc.lnpchain[g * sc.tcap + sc.tcol] = sc.lnp[g];
+}
+
+// bytes of the exchange block: pos [rows][ndim], lnp [rows], then kMaxPeers + 2 ints (flags, ticket, error)
+size_t split_block_bytes(size_t rows, int ndim) {
+    return (rows * ndim + rows) * sizeof(double) + (nmb::kMaxPeers + 2) * sizeof(int) + 8;
 }
 
 int sampler_reserve(nmb_sampler* s, int64_t need) {
@@ -1057,7 +621,11 @@ int sampler_check_nan(nmb_sampler* s, const char* what) {
 
 extern "C" void nmb_sampler_destroy(nmb_sampler* s) {
     if (!s) return;
-    cudaFree(s->d_pos); cudaFree(s->d_lnp); cudaFree(s->d_q); cudaFree(s->d_zz); cudaFree(s->d_logu);
+    if (s->st) cudaStreamSynchronize(s->st);
+    for (void* pb : s->peer_base)
+        if (pb) cudaIpcCloseMemHandle(pb);
+    cudaFree(s->d_xchg);  // pos, lnp and the split flags
+    cudaFree(s->d_q); cudaFree(s->d_zz); cudaFree(s->d_logu);
     cudaFree(s->d_chain); cudaFree(s->d_lnpchain); cudaFree(s->d_priors); cudaFree(s->d_nacc); cudaFree(s->d_nan);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
@@ -1075,9 +643,16 @@ static int sampler_create_impl(nmb_lc* lc, int64_t W, int ndim, const double* pr
     s->lc = lc; s->W = W; s->C = lc->ncand; s->mode = mode; s->a = a; s->seed = seed; s->ndim = ndim;
     const size_t rows = (size_t)s->C * W, hrows = (size_t)s->C * (W / 2);
     cudaError_t e = cudaSuccess;
-    if ((e = cudaMalloc(&s->d_pos, rows * ndim * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&s->d_lnp, rows * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&s->d_q, hrows * ndim * sizeof(double))) != cudaSuccess ||
+    const size_t xchg_bytes = split_block_bytes(rows, ndim);
+    if ((e = cudaMalloc(&s->d_xchg, xchg_bytes)) != cudaSuccess ||
+        (e = cudaMemset(s->d_xchg, 0, xchg_bytes)) != cudaSuccess) {
+        nmb_sampler_destroy(s);
+        return cuda_fail(e, "nmb_sampler_create");
+    }
+    s->d_pos = s->d_xchg;
+    s->d_lnp = s->d_xchg + rows * ndim;
+    s->d_flags = reinterpret_cast<int*>(s->d_xchg + rows * ndim + rows);
+    if ((e = cudaMalloc(&s->d_q, hrows * ndim * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_zz, hrows * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_logu, hrows * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&s->d_nacc, rows * sizeof(long long))) != cudaSuccess ||
@@ -1200,6 +775,128 @@ extern "C" int nmb_sampler_run(nmb_sampler* s, int64_t nsteps, int64_t thin, int
         if (st_col) s->tlen += 1;
     }
     return sampler_check_nan(s, "lnprob returned NaN.");
+}
+
+
+// ---- one ensemble split by walker over several GPUs (BASELINE config 5) ---------------------------------
+// see split_kernels.cuh for the protocol
+extern "C" int nmb_sampler_split_export(nmb_sampler* s, void* handle_out) {
+    if (!s || !handle_out) return fail(NMB_ERR_ARG, "nmb_sampler_split_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NMB_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->d_xchg));
+    std::memcpy(handle_out, &h, sizeof h);
+    return NMB_OK;
+}
+
+extern "C" int nmb_sampler_split_attach(nmb_sampler* s, int rank, int world, const void* handles) {
+    if (!s || !handles) return fail(NMB_ERR_ARG, "nmb_sampler_split_attach: null pointer");
+    if (s->C != 1) return fail(NMB_ERR_ARG, "nmb_sampler_split_attach: the walker split works on a single light curve");
+    if (world < 1 || world > nmb::kMaxPeers || rank < 0 || rank >= world)
+        return fail(NMB_ERR_ARG, "nmb_sampler_split_attach: rank / world out of range (at most 16 ranks)");
+    if ((s->W / 2) % world) return fail(NMB_ERR_ARG, "nmb_sampler_split_attach: half the ensemble must divide evenly over the ranks");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank || s->peer_base[r]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + (size_t)r * NMB_IPC_HANDLE_BYTES, sizeof h);
+        cudaError_t e = cudaIpcOpenMemHandle(&s->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            s->peer_base[r] = nullptr;
+            return cuda_fail(e, "nmb_sampler_split_attach: cudaIpcOpenMemHandle (peer access between the GPUs is required)");
+        }
+    }
+    s->split_rank = rank;
+    s->split_world = world;
+    return NMB_OK;
+}
+
+static nmb::SplitPeers split_peers(const nmb_sampler* s) {
+    nmb::SplitPeers pp{};
+    pp.world = s->split_world;
+    pp.rank = s->split_rank;
+    const size_t rows = (size_t)s->C * s->W;
+    for (int r = 0; r < s->split_world; ++r) {
+        double* base = static_cast<double*>(s->peer_base[r]);
+        if (!base) continue;
+        pp.pos[r] = base;
+        pp.lnp[r] = base + rows * s->ndim;
+        pp.flags[r] = reinterpret_cast<int*>(base + rows * s->ndim + rows);
+    }
+    return pp;
+}
+
+// nsteps steps of the split sampler: per half-step this rank's slice [k0, k0 + nk) of the active half is
+// updated (two launches), pushed into every peer's replica and the arrival flags are exchanged (one launch).
+// No host round trip and no NCCL call inside the loop; synchronises once at the end.
+extern "C" int nmb_sampler_run_split(nmb_sampler* s, int64_t nsteps, int store_all) {
+    if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_run_split: null pointer");
+    if (!s->has_state) return fail(NMB_ERR_ARG, "Cannot have pos0=None if run_mcmc has never been called.");
+    if (nsteps < 0) return fail(NMB_ERR_ARG, "nmb_sampler_run_split: nsteps < 0");
+    const int world = s->split_world, rank = s->split_rank;
+    for (int r = 0; r < world; ++r)
+        if (r != rank && !s->peer_base[r]) return fail(NMB_ERR_ARG, "nmb_sampler_run_split: peers are not attached");
+    const int64_t halfk = s->W / 2, nk = halfk / world, k0 = rank * nk;
+    if (store_all)
+        if (int rc = sampler_reserve(s, s->tlen + nsteps)) return rc;
+    const nmb::SplitPeers pp = split_peers(s);
+    static const double tmo_s = std::getenv("NMB_SPLIT_TIMEOUT_S") ? std::atof(std::getenv("NMB_SPLIT_TIMEOUT_S")) : 10.0;
+    const unsigned long long timeout_ns = (unsigned long long)(tmo_s * 1e9);
+    const int xblocks = (int)std::max<int64_t>(1, std::min<int64_t>(32, (nk * s->ndim + 1023) / 1024));
+    for (int64_t i = 0; i < nsteps; ++i) {
+        for (int half = 0; half < 2; ++half) {
+            const nmb::SampleCtx sc = sampler_ctx(s, half, (int)k0, 0);
+            if (int rc = sampler_eval(s, s->d_q, nk, nullptr, sc)) return rc;
+            if (world > 1) {
+                const int epoch = (int)(++s->split_epoch);
+                CU(launch_pdl(nmb::split_exchange_kernel, dim3(xblocks), dim3(256), 0, s->st, pp, (const double*)s->d_pos,
+                              (const double*)s->d_lnp, s->ndim, (long long)(half * halfk + k0), (int)nk, epoch, s->d_flags,
+                              timeout_ns));
+                g_launches++;
+            }
+        }
+        if (store_all) {
+            const nmb::SampleCtx sc = sampler_ctx(s, 0, 0, 1);
+            const long long n = (long long)s->C * s->W;
+            append_chain_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->st>>>(sc, n);
+            g_launches++;
+            CU(cudaGetLastError());
+            s->tlen += 1;
+        }
+        s->step += 1;
+    }
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, s->d_flags + nmb::kMaxPeers + 1, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    if (err) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "nmb_sampler_run_split: rank %d did not arrive within the time-out", err - 1);
+        return fail(NMB_ERR_CUDA, buf);
+    }
+    return sampler_check_nan(s, "lnprob returned NaN.");
+}
+
+// NCCL transport of the same exchange: this rank's slice of a half as [nk][ndim + 1] rows (device), and the
+// gathered [world][nk][ndim + 1] rows back into the replica.  Both run in the sampler's stream.
+extern "C" int nmb_sampler_pack_half(nmb_sampler* s, int half, int64_t k0, int64_t nk, double* out) {
+    if (!s || !out) return fail(NMB_ERR_ARG, "nmb_sampler_pack_half: null pointer");
+    if (s->C != 1) return fail(NMB_ERR_ARG, "nmb_sampler_pack_half: single light curve only");
+    if (half < 0 || half > 1 || k0 < 0 || nk < 1 || k0 + nk > s->W / 2) return fail(NMB_ERR_ARG, "nmb_sampler_pack_half: bad slice");
+    const long long n = (long long)nk * (s->ndim + 1);
+    nmb::split_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s->st>>>(s->d_pos, s->d_lnp, s->ndim,
+                                                                         (long long)(half * (s->W / 2) + k0), (int)nk, out);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
+}
+extern "C" int nmb_sampler_unpack_half(nmb_sampler* s, int half, const double* in) {
+    if (!s || !in) return fail(NMB_ERR_ARG, "nmb_sampler_unpack_half: null pointer");
+    if (s->C != 1) return fail(NMB_ERR_ARG, "nmb_sampler_unpack_half: single light curve only");
+    if (half < 0 || half > 1) return fail(NMB_ERR_ARG, "nmb_sampler_unpack_half: bad half");
+    const long long halfk = s->W / 2, n = halfk * (s->ndim + 1);
+    nmb::split_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s->st>>>(s->d_pos, s->d_lnp, s->ndim, half * halfk, halfk, in);
+    g_launches++;
+    CU(cudaGetLastError());
+    return NMB_OK;
 }
 
 extern "C" int nmb_sampler_sync(nmb_sampler* s) {

@@ -533,7 +533,7 @@ template <int PATH>
 __device__ __forceinline__ double sample_flux_eval(double ti, double offk, const WalkerConsts& wc,
                                                    const QuadConstsF& cf, const QuadConsts* gq);
 
-__device__ __noinline__ double sample_flux_slowpath(double z, const QuadConsts* q) {
+static __device__ __noinline__ double sample_flux_slowpath(double z, const QuadConsts* q) {
     return occultquad_point<false, IeeeOps>(z, *q, nullptr, nullptr, nullptr);
 }
 
@@ -1064,7 +1064,7 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
                                        [&]() { return oot_words.value(); });
 }
 
-__global__ void init_ranges_kernel(int* rlo, int* rhi, int* itemsdone, int n) {
+static __global__ void init_ranges_kernel(int* rlo, int* rhi, int* itemsdone, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { rlo[i] = INT_MAX; rhi[i] = 0; itemsdone[i] = 0; }
 }

@@ -106,6 +106,7 @@ gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restr
     // the quadratic form.  Both differ from the textbook evaluation by rounding only.
     double D = 0.0, rD = 0.0, z = 0.0, quad = 0.0, tprev = 0.0, mant = 1.0;
     long long esum = 0;
+    bool indefinite = false;  // a pivot D_n <= 0 (or NaN): celerite's solver raises LinAlgError there
     for (int i = 0; i < n; ++i) {
         const double ti = __ldg(gt + i);
         const double mean = (i >= lo && i < hi) ? gm[i] : 1.0;
@@ -158,6 +159,7 @@ gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restr
             z = r - uf;
         }
         quad += (z * z) * rD;
+        indefinite |= !(D > 0.0);
         int e2;
         mant *= frexp(D, &e2);
         esum += e2;
@@ -168,7 +170,9 @@ gp_solve_kernel(LcView lc, const double* __restrict__ var, const double* __restr
         tprev = ti;
     }
     const double logdet = log(mant) + (double)esum * 0.6931471805599453;
-    const double ll = -0.5 * ((quad + logdet) + n * 1.8378770664093453);  // log(2 pi)
+    // not positive definite: -inf, what celerite's log_likelihood(quiet=True) returns (an even number of
+    // negative pivots would otherwise give a finite value the sampler could accept)
+    const double ll = indefinite ? -INFINITY : -0.5 * ((quad + logdet) + n * 1.8378770664093453);  // log(2 pi)
     const double lp = priors ? ln_prior_dev(par, priors + (long long)cand * gs.ndim * 6, gs.ndim) : 0.0;
     finish_walker(sc, cw, W, ll, lp, lnprob, loglike);
     // leave the range workspace idle for the next evaluation

@@ -476,7 +476,7 @@ lnprob_window_kernel(LcView lc, const double* __restrict__ params, int W, const 
 }
 
 // ---- element-wise helpers ---------------------------------------------------------------
-__global__ void occultquad_array_kernel(const double* __restrict__ z, long long n, double rprs, double ld1,
+static __global__ void occultquad_array_kernel(const double* __restrict__ z, long long n, double rprs, double ld1,
                                         double ld2, double* __restrict__ out) {
     const QuadConsts qc = make_quad_consts(rprs, ld1, ld2);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -490,14 +490,14 @@ __global__ void occultquad_array_kernel(const double* __restrict__ z, long long 
     }
 }
 
-__global__ void lnprior_kernel(const double* __restrict__ params, long long W, int npar,
+static __global__ void lnprior_kernel(const double* __restrict__ params, long long W, int npar,
                                const double* __restrict__ priors, double* __restrict__ out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < W) out[i] = ln_prior_dev(params + i * npar, priors, npar);
 }
 
 // DFMA throughput probe: 8 independent chains per thread
-__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+static __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; ++i) {
         x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);

@@ -5,8 +5,9 @@
     data-path collective -- :func:`shard_candidates`.
 (b) One large ensemble split by walker (BASELINE config 5): every rank holds the full light curve
     and a replica of the ensemble, updates its slice of the active half-ensemble, and the slices
-    are all-gathered (NCCL over NVLink) after each half-step -- :class:`WalkerSplit`,
-    :func:`allgather_half`, :class:`SplitEnsembleSampler`.  Because the random stream is keyed by
+    reach the other replicas after each half-step -- by device-side stores into the peers' memory over
+    NVLink (default) or by one packed NCCL all-gather -- :class:`WalkerSplit`, :func:`allgather_half`,
+    :class:`SplitEnsembleSampler`.  Because the random stream is keyed by
     (seed, step, half, walker), the chain is bit-identical for any number of ranks.
 
 The reference has no collective at all (its only parallelism is emcee's process pool,
@@ -44,16 +45,20 @@ class WalkerSplit(object):
 
 
 def allgather_half(pos, lnp, half, split, group=None):
-    """All-gather the slices of half-ensemble `half` that each rank just updated, in place.
-    `pos` [W, ndim] and `lnp` [W] are torch tensors (CUDA with NCCL, CPU with gloo)."""
+    """All-gather the slices of half-ensemble `half` that each rank just updated, in place, as ONE packed
+    collective: rows [nk, ndim + 1] (position, lnprob) per rank.  `pos` [W, ndim] and `lnp` [W] are torch
+    tensors (CPU with gloo in the tests; the CUDA path of SplitEnsembleSampler packs with its own kernels)."""
+    import torch
     import torch.distributed as dist
     if split.world == 1:
         return
     r0, nk = split.rows(half)
-    for full, trailing in ((pos, pos.shape[1:]), (lnp, ())):
-        mine = full[r0:r0 + nk].clone()
-        outs = [full[split.rows(half, r)[0]:split.rows(half, r)[0] + nk] for r in range(split.world)]
-        dist.all_gather(outs, mine, group=group)
+    mine = torch.cat([pos[r0:r0 + nk], lnp[r0:r0 + nk, None]], dim=1).contiguous()
+    full = torch.empty((split.world * nk, mine.shape[1]), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    h0 = half * split.halfk
+    pos[h0:h0 + split.halfk] = full[:, :-1]
+    lnp[h0:h0 + split.halfk] = full[:, -1]
 
 
 class _DevArray(object):
@@ -66,12 +71,23 @@ class _DevArray(object):
 
 class SplitEnsembleSampler(object):
     """Walker-split ensemble sampler: same chain as :class:`namaste_b200.EnsembleSampler` with the
-    same seed, computed by `world` GPUs.  Requires an initialised torch.distributed process group."""
+    same seed, computed by `world` GPUs of one node (one process per GPU, initialised torch.distributed
+    process group).
 
-    def __init__(self, lightcurve, priors, nwalkers, seed, mode="windowed", a=2.0, group=None):
+    ``transport`` selects how the updated half-ensemble slices reach the other ranks:
+
+    * ``"p2p"``  -- device side: every rank maps its peers' ensemble replicas through CUDA IPC, a kernel stores
+      the slice into every replica over NVLink and exchanges arrival flags (csrc/split_kernels.cuh).  The whole
+      run is one C call: no NCCL launch, no Python and no host synchronisation per step.
+    * ``"nccl"`` -- one packed ``all_gather_into_tensor`` of [nk, ndim + 1] rows per half-step.
+    * ``"auto"`` (default) -- ``"p2p"`` when every rank can map its peers, else ``"nccl"`` (with a warning)."""
+
+    def __init__(self, lightcurve, priors, nwalkers, seed, mode="windowed", a=2.0, group=None, transport="auto"):
         import torch
         import torch.distributed as dist
         from . import core
+        if transport not in ("auto", "p2p", "nccl"):
+            raise ValueError("transport must be 'auto', 'p2p' or 'nccl'")
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -89,6 +105,36 @@ class SplitEnsembleSampler(object):
         self.pos = torch.as_tensor(_DevArray(lib.nmb_sampler_devptr(h, 0), (self.W, 6)), device="cuda")
         self.lnp = torch.as_tensor(_DevArray(lib.nmb_sampler_devptr(h, 1), (self.W,)), device="cuda")
         self.iterations = 0
+        self.transport = "local" if self.world == 1 else self._connect(transport)
+        if self.transport == "nccl":
+            self._send = torch.empty((self.split.nk, 7), dtype=torch.float64, device="cuda")
+            self._recv = torch.empty((self.split.halfk, 7), dtype=torch.float64, device="cuda")
+
+    def _connect(self, transport):
+        """Exchange the CUDA IPC handles of the ensemble replicas and map the peers; every rank takes the same
+        transport (the outcome is agreed with an all-reduce)."""
+        import warnings
+        import torch
+        import torch.distributed as dist
+        if transport == "nccl":
+            return "nccl"
+        lib = load()
+        mine = np.zeros(64, dtype=np.uint8)
+        check(lib.nmb_sampler_split_export(self._h, ptr(mine)), "SplitEnsembleSampler")
+        send = torch.from_numpy(mine).cuda()
+        recv = torch.empty(64 * self.world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        handles = np.ascontiguousarray(recv.cpu().numpy())
+        rc = lib.nmb_sampler_split_attach(self._h, self.rank, self.world, ptr(handles))
+        why = load().nmb_last_error().decode("utf-8", "replace") if rc else ""
+        ok = torch.tensor([0 if rc else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            return "p2p"
+        if transport == "p2p":
+            raise RuntimeError("SplitEnsembleSampler: peer mapping failed on at least one rank (%s)" % (why or "another rank"))
+        warnings.warn("SplitEnsembleSampler: peer mapping unavailable (%s); using the NCCL transport" % (why or "another rank"))
+        return "nccl"
 
     def __del__(self):
         try:
@@ -100,21 +146,27 @@ class SplitEnsembleSampler(object):
 
     def run_mcmc(self, pos0, nsteps, storechain=True):
         """Advance the replicated ensemble `nsteps` steps.  Everything of a step -- the rank's slice of
-        each half-ensemble (two launches), the all-gather of the updated slices, the chain append --
+        each half-ensemble (two launches), the exchange of the updated slices, the chain append --
         is ordered on the sampler's CUDA stream; the host only waits once, at the end."""
         import torch
+        import torch.distributed as dist
         lib = load()
         if pos0 is not None:
             check(lib.nmb_sampler_set_state(self._h, ptr(as_f64(pos0)), None), "run_mcmc")
         sp = self.split
-        stream = torch.cuda.ExternalStream(int(lib.nmb_sampler_stream(self._h)))
-        with torch.cuda.stream(stream):
-            for _ in range(int(nsteps)):
-                for half in (0, 1):
-                    check(lib.nmb_sampler_halfstep(self._h, half, sp.k0, sp.nk, 0), "run_mcmc")
-                    allgather_half(self.pos, self.lnp, half, sp, self.group)   # NCCL orders itself after / before this stream
-                check(lib.nmb_sampler_advance(self._h, 0, 1 if storechain else 0), "run_mcmc")
-        check(lib.nmb_sampler_sync(self._h), "run_mcmc")      # one host wait + NaN check (emcee: ValueError)
+        if self.transport in ("local", "p2p"):
+            check(lib.nmb_sampler_run_split(self._h, int(nsteps), 1 if storechain else 0), "run_mcmc")
+        else:
+            stream = torch.cuda.ExternalStream(int(lib.nmb_sampler_stream(self._h)))
+            with torch.cuda.stream(stream):
+                for _ in range(int(nsteps)):
+                    for half in (0, 1):
+                        check(lib.nmb_sampler_halfstep(self._h, half, sp.k0, sp.nk, 0), "run_mcmc")
+                        check(lib.nmb_sampler_pack_half(self._h, half, sp.k0, sp.nk, ptr(self._send)), "run_mcmc")
+                        dist.all_gather_into_tensor(self._recv, self._send, group=self.group)  # ordered on this stream
+                        check(lib.nmb_sampler_unpack_half(self._h, half, ptr(self._recv)), "run_mcmc")
+                    check(lib.nmb_sampler_advance(self._h, 0, 1 if storechain else 0), "run_mcmc")
+            check(lib.nmb_sampler_sync(self._h), "run_mcmc")      # one host wait + NaN check (emcee: ValueError)
         self.iterations += int(nsteps)
         return self.pos.cpu().numpy(), self.lnp.cpu().numpy()
 

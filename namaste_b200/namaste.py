@@ -19,7 +19,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-from . import core
+from . import core, _lib
 
 __all__ = ["MonotransitModel", "MonoLnPrior", "MonoOnlyLogProb", "MonoOnlyNegLogProb", "CalcTdur", "CalcVel",
            "stage_lightcurve", "clear_cache", "calcminp", "calcmaxvel", "monoPriors", "initLD", "BuildMeanPriors",
@@ -30,22 +30,22 @@ _LC_CACHE_MAX = 8
 
 
 def _fingerprint(a):
-    """Identity + content key of an array: address and layout, plus two wrap-around checksums over EVERY
-    64-bit word of its float64 image, the plain sum and the sum weighted by the odd numbers (which makes
-    it sensitive to position); ~20 us for a 4000-point light curve.  A sampled probe is not enough: a
-    light curve re-detrended in place, or a new array that lands on a freed address with the same times
-    and errors, differs from the staged one only in some flux values."""
-    bits = np.ascontiguousarray(a, dtype=np.float64).reshape(-1).view(np.uint64)
-    odd = _ODD.get(bits.size)
-    if odd is None:
-        if len(_ODD) >= 4:   # a few light-curve lengths at most (12 MB per 500 k-point entry)
-            _ODD.clear()
-        odd = _ODD[bits.size] = (np.arange(bits.size, dtype=np.uint64) << np.uint64(1)) | np.uint64(1)
-    return (a.__array_interface__["data"][0], a.shape, a.strides,
-            int(np.add.reduce(bits, dtype=np.uint64)), int(np.dot(bits, odd)))
-
-
-_ODD = {}
+    """Identity + content key of a light-curve array: address and layout, plus a position-sensitive checksum
+    over EVERY 64-bit word of its float64 image (nmb_host_checksum: one pass at memory speed, ~2 us for a
+    4000-point light curve, ~1 ms for 500 000 points).  A sampled probe is not enough: a light curve
+    re-detrended in place, or a new array that lands on a freed address with the same times and errors,
+    differs from the staged one only in some flux values.  An array that cannot change under the caller --
+    ``writeable`` False on it and on its base -- is keyed by identity alone (``lc.setflags(write=False)`` is
+    the cheap way to call MonoOnlyLogProb with a raw array in a loop; passing the staged LightCurve is free)."""
+    ident = (a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
+    base = a.base
+    if not a.flags.writeable and (base is None or not getattr(getattr(base, "flags", None), "writeable", True)):
+        return ident
+    img = a if (a.dtype == np.float64 and a.flags.c_contiguous) else np.ascontiguousarray(a, dtype=np.float64)
+    out = np.zeros(2, dtype=np.uint64)
+    lib = _lib.load()
+    _lib.check(lib.nmb_host_checksum(_lib.ptr(img), img.size, _lib.ptr(out)), "stage_lightcurve")
+    return ident + (int(out[0]), int(out[1]))
 
 
 def stage_lightcurve(lc, oversamp=10):
@@ -63,16 +63,16 @@ def stage_lightcurve(lc, oversamp=10):
         return hit
     staged = core.LightCurve(np.ascontiguousarray(lc, dtype=np.float64), oversamp=oversamp)
     _LC_CACHE[key] = staged
+    # Eviction only drops the cache's reference: a live EnsembleSampler keeps the raw handle of its
+    # LightCurve, so the device memory must stay until the last Python reference goes (LightCurve.__del__).
     while len(_LC_CACHE) > _LC_CACHE_MAX:
-        _, old = _LC_CACHE.popitem(last=False)
-        old.close()
+        _LC_CACHE.popitem(last=False)
     return staged
 
 
 def clear_cache():
-    while _LC_CACHE:
-        _, old = _LC_CACHE.popitem()
-        old.close()
+    """Forget every staged light curve (their device memory is freed once nothing else refers to them)."""
+    _LC_CACHE.clear()
 
 
 class MonotransitModel(object):
@@ -349,23 +349,30 @@ class _BatchedObjective(object):
         self.results = {}
         self.generation = 0
         self.ncalls = 0
+        self.error = None
 
     def _flush(self):
         keys = list(self.pending.keys())
-        rows = np.concatenate([self.pending[k] for k in keys], axis=0)
-        vals = self.evaluate(rows)
-        self.ncalls += 1
-        at = 0
-        for k in keys:
-            n = len(self.pending[k])
-            self.results[k] = vals[at:at + n]
-            at += n
-        self.pending.clear()
-        self.generation += 1
-        self.cv.notify_all()
+        try:
+            rows = np.concatenate([self.pending[k] for k in keys], axis=0)
+            vals = self.evaluate(rows)
+            self.ncalls += 1
+            at = 0
+            for k in keys:
+                n = len(self.pending[k])
+                self.results[k] = vals[at:at + n]
+                at += n
+        except BaseException as exc:  # a failed GPU call must wake every waiting optimiser, not strand it
+            self.error = exc
+        finally:
+            self.pending.clear()
+            self.generation += 1
+            self.cv.notify_all()
 
     def call(self, key, rows):
         with self.cv:
+            if self.error is not None:
+                raise self.error
             self.pending[key] = rows
             if len(self.pending) == self.active:
                 self._flush()
@@ -373,6 +380,8 @@ class _BatchedObjective(object):
                 gen = self.generation
                 while self.generation == gen:
                     self.cv.wait()
+            if self.error is not None:
+                raise self.error
             return self.results.pop(key)
 
     def leave(self):
@@ -423,6 +432,8 @@ def Optimize_mono(flatlc, priors, starts, tcen=None, tdur=None, monomodel=None, 
         th.start()
     for th in threads:
         th.join()
+    if batch.error is not None:
+        raise batch.error
     suc = [np.hstack((r.x, r.fun)) for r in results if r is not None and r.success]
     if len(suc) == 0:
         raise ValueError("No successful Monotransit minimizations")
@@ -466,13 +477,18 @@ def PlanetRtoM(Rad):
     return M
 
 
-def MonoFinalPars(samples, srads, smasss, sdenss, rows=None, sigs=(15.865525393145707, 50.0, 84.13447460685429)):
+def MonoFinalPars(samples, srads, smasss, sdenss, rows=None, sigs=(15.865525393145707, 50.0, 84.13447460685429),
+                  rng=None):
     """Derived planet quantities of Star.MonoFinalPars (namaste.py:629-652) for sample rows ``rows`` of
     ``samples`` [n, >=4] (tcen, b, vel, RpRs, ...) paired with the stellar PDFs: planet radius [Rearth],
     semi-major axis [AU], period [d], mass [Mearth], RV semi-amplitude [m/s]; returns the PDFs and
-    (median, +err, -err) of each."""
+    (median, +err, -err) of each.  By default the rows are drawn like the reference draws them,
+    ``choice(len(samples), npdf, replace=False)`` (namaste.py:636) from ``rng`` (``np.random`` if None):
+    samples are walker-major, so the first npdf rows would be one autocorrelated stretch of one chain."""
     samples = np.asarray(samples, dtype=np.float64)
-    rows = np.arange(len(srads)) if rows is None else np.asarray(rows)
+    if rows is None:
+        rows = (np.random if rng is None else rng).choice(len(samples), len(srads), replace=False)
+    rows = np.asarray(rows)
     out = {}
     out["Rps"] = (samples[rows, 3] * 695500000 * srads) / 6.371e6
     out["Prob_pl"] = len(out["Rps"][out["Rps"] < (1.5 * 11.2)]) / len(out["Rps"])

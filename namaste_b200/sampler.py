@@ -107,6 +107,8 @@ class EnsembleSampler(object):
         """Advance the ensemble N steps from pos0 (or from where the last call stopped if None).
         Returns (pos, lnprob, rstate) like emcee 2.x; rstate is the (seed, step) pair of the stream."""
         lib = load()
+        if not getattr(self._lc, "_h", None):
+            raise ValueError("the LightCurve of this sampler has been closed")
         self._ensure(rstate0)
         if pos0 is None:
             if not self._have_state:

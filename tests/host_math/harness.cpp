@@ -6,7 +6,7 @@
 #define __device__
 #define __forceinline__ inline
 #define __noinline__
-#define __constant__ static const
+#define __constant__ const
 #define __launch_bounds__(...)
 #include <cmath>
 #include <cstdint>

@@ -24,16 +24,24 @@ def main():
     rng = np.random.default_rng(11)
     W, nsteps, seed = 64, 8, 987654321
     pos0 = g["theta"][None, :] * (1 + 1e-4 * rng.standard_normal((W, 6)))
-    split = SplitEnsembleSampler(lc, g["priors"], W, seed)
-    split.run_mcmc(pos0, nsteps)
-    chain, lnpc, nacc = split.chain, split.lnprobability, split.naccepted
     ok = True
+    single = None
     if rank == 0:
         single = nb.EnsembleSampler(W, 6, nb.MonoOnlyLogProb, args=(lc, g["priors"]), seed=seed)
         single.run_mcmc(pos0, nsteps)
-        ok = (np.array_equal(chain, single.chain) and np.array_equal(lnpc, single.lnprobability)
-              and np.array_equal(nacc, single.naccepted))
-        print("MULTIGPU_CHECK world=%d bitwise_equal=%s acceptance=%.3f" % (world, ok, nacc.mean() / nsteps), flush=True)
+    for transport in ("auto", "nccl"):
+        split = SplitEnsembleSampler(lc, g["priors"], W, seed, transport=transport)
+        split.run_mcmc(pos0, nsteps // 2)
+        split.run_mcmc(None, nsteps - nsteps // 2)      # a second call continues the chain (emcee contract)
+        chain, lnpc, nacc = split.chain, split.lnprobability, split.naccepted
+        if rank == 0:
+            same = (np.array_equal(chain, single.chain) and np.array_equal(lnpc, single.lnprobability)
+                    and np.array_equal(nacc, single.naccepted))
+            ok = ok and same
+            print("MULTIGPU_CHECK world=%d transport=%s(%s) bitwise_equal=%s acceptance=%.3f" % (
+                world, transport, split.transport, same, nacc.mean() / nsteps), flush=True)
+        dist.barrier()
+        del split
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -20,4 +20,4 @@ def test_walker_split_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multigpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "bitwise_equal=True" in res.stdout
+    assert res.stdout.count("bitwise_equal=True") == 2 and "bitwise_equal=False" not in res.stdout

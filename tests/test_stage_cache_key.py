@@ -27,3 +27,16 @@ def test_fingerprint_layouts():
     assert _fingerprint(lc) != _fingerprint(lc.copy())            # different address
     assert _fingerprint(lc[::2]) != _fingerprint(lc[:5])          # different strides / content
     assert _fingerprint(lc.astype(np.float32))[1] == (10, 3)      # other dtypes are keyed on their float64 image
+
+
+def test_readonly_array_is_keyed_by_identity():
+    lc = np.arange(30, dtype=np.float64).reshape(10, 3).copy()    # owns its data
+    full = _fingerprint(lc)
+    lc.setflags(write=False)
+    assert _fingerprint(lc) == full[:4]                            # no content pass for an immutable array
+    view = lc[:5]                                                  # read-only view of a read-only base
+    assert len(_fingerprint(view)) == 4
+    rw = np.arange(30, dtype=np.float64).reshape(10, 3)
+    ro_view = rw[:]
+    ro_view.setflags(write=False)                                  # the base can still change under it
+    assert len(_fingerprint(ro_view)) == 6
