@@ -772,6 +772,8 @@ _REAL_STDOUT = 1
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()   # a crash inside the library shows the Python frame it came from (stderr)
     # Libraries (NCCL's version banner, torchrun notices) write to fd 1; the driver expects exactly
     # one JSON line there, so everything else is diverted to stderr.
     global _REAL_STDOUT

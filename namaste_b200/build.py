@@ -41,17 +41,22 @@ def _stale():
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu -> namaste_b200/libnamaste_b200.so (skipped when up to date)."""
-    if not force and not _stale():
+def build_library(force=False, verbose=False, extra_flags=(), out=None, sources=None):
+    """Compile csrc/*.cu -> namaste_b200/libnamaste_b200.so (skipped when up to date).
+    `extra_flags` / `out` build an experimental variant beside it (A/B runs through NMB_LIB)."""
+    variant = out is not None or bool(extra_flags)
+    if not variant and not force and not _stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
-    os.makedirs(OBJDIR, exist_ok=True)
+    lib = out or LIB
+    objdir = OBJDIR if not variant else os.path.join(OBJDIR, os.path.splitext(os.path.basename(lib))[0])
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", "-o", obj, os.path.join(CSRC, src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
@@ -61,14 +66,17 @@ def build_library(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB + ".tmp"
+    tmp = lib + ".tmp"
     res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs,
                          capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, lib)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m namaste_b200.build [--force] [-v] [--out path.so -DNAME=VALUE ...]
+    flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=flags, out=out))

@@ -8,6 +8,8 @@
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::mutex g_live_mu;
+std::set<const void*> g_live_lc;
 
 extern "C" const char* nmb_last_error(void) { return g_err.c_str(); }
 extern "C" const char* nmb_version(void) { return "namaste_b200 0.1 (sm_100a)"; }
@@ -15,6 +17,10 @@ extern "C" int64_t nmb_launch_count(void) { return g_launches.load(); }
 
 extern "C" void nmb_lc_destroy(nmb_lc* lc) {
     if (!lc) return;
+    {
+        std::lock_guard<std::mutex> g(g_live_mu);
+        g_live_lc.erase(lc);
+    }
     cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_term); cudaFree(lc->d_var); cudaFree(lc->d_modelbuf); cudaFree(lc->d_meanpar); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
     cudaFree(lc->d_tgrid); cudaFree(lc->d_gcount); cudaFree(lc->d_t0); cudaFree(lc->d_ginv);
     cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
@@ -168,6 +174,10 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
         (e = cudaStreamCreateWithFlags(&lc->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         nmb_lc_destroy(lc);
         return cuda_fail(e, "nmb_lc_create: staging");
+    }
+    {
+        std::lock_guard<std::mutex> g(g_live_mu);
+        g_live_lc.insert(lc);
     }
     *out = lc;
     return NMB_OK;
@@ -621,7 +631,12 @@ int sampler_check_nan(nmb_sampler* s, const char* what) {
 
 extern "C" void nmb_sampler_destroy(nmb_sampler* s) {
     if (!s) return;
-    if (s->st) cudaStreamSynchronize(s->st);
+    if (s->st) {
+        cudaStreamSynchronize(s->st);
+        // the light curve remembers the last stream that used its workspace: forget this one before it is destroyed
+        std::lock_guard<std::mutex> g(g_live_mu);
+        if (g_live_lc.count(s->lc) && s->lc->ws_last_stream == s->st) s->lc->ws_used = false;
+    }
     for (void* pb : s->peer_base)
         if (pb) cudaIpcCloseMemHandle(pb);
     cudaFree(s->d_xchg);  // pos, lnp and the split flags

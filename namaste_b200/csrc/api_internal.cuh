@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -18,6 +19,9 @@
 
 extern thread_local std::string g_err;
 extern std::atomic<long long> g_launches;
+// live light-curve handles: a sampler that is destroyed after its light curve must not touch it
+extern std::mutex g_live_mu;
+extern std::set<const void*> g_live_lc;
 
 inline int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -36,6 +40,10 @@ constexpr int kThreads = 128;  // sweep / window block size
 constexpr int kTPT = 4;        // timestamps per thread in the sweep -> 512-timestamp tiles
 constexpr int kTile = kThreads * kTPT;
 constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-thread sweep
+#ifndef NMB_SWEEP_MINB
+#define NMB_SWEEP_MINB 7         // resident 128-walker sweep blocks per SM (72 registers: no spills with four timestamps per trip;
+                                 // measured on the 65 k x 4096 sweep: 0.664 ms against 0.692 at 8 blocks and 0.671 at 6)
+#endif
 
 // Per-stage device timing (nmb_stage_timing / nmb_stage_times): CUDA events around stage 1 and
 // stage 2 of every evaluation on the launching stream.  The event between the two kernels keeps
@@ -121,8 +129,6 @@ struct nmb_lc {
         if (ws_used && st != ws_last_stream) {
             if (!ws_event && cudaEventCreateWithFlags(&ws_event, cudaEventDisableTiming) != cudaSuccess) return NMB_ERR_CUDA;
             if (cudaEventRecord(ws_event, ws_last_stream) != cudaSuccess || cudaStreamWaitEvent(st, ws_event, 0) != cudaSuccess) {
-                // the previous stream is gone (its sampler was destroyed, which synchronised it): nothing of it
-                // can still be running, but be safe
                 cudaGetLastError();
                 if (cudaDeviceSynchronize() != cudaSuccess) {
                     g_err = "nmb: could not order the evaluation behind the previous stream";
@@ -364,7 +370,7 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     const long long blocks128 = (long long)lc->ncand * ((W + 127) / 128) * lc->ngran;
     const bool wide = force_thr ? (force_thr == 128) : (W >= 128 || blocks128 >= 4 * 148);
     int rc = !wide ? launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc)
-                   : launch_sweep_t<S, 128, 8>(lc, params, W, priors, lnprob, loglike, st, sc);
+                   : launch_sweep_t<S, 128, NMB_SWEEP_MINB>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (rc) return rc;
     lc->timer.mark(1, st);
     rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)

@@ -187,6 +187,26 @@ struct WalkSmem {
     int flag;
 };
 
+// min over the S supersamples of one timestamp of hi32(q'), q' = fma(vx', vx', b^2), vx' = fma(vel, t_i, ck[k]):
+// 2 S DFMA and ceil(S / 2) three-input integer minima
+template <int S>
+__device__ __forceinline__ int sweep_qmin(double vel, double ti, const double (&ck)[S > 0 ? S : 1], double b2) {
+    int h[S > 0 ? S : 1];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        const double vx = fma(vel, ti, ck[k]);
+        h[k] = __double2hiint(fma(vx, vx, b2));
+    }
+    int qmin = (S & 1) ? h[S - 1] : min(h[S - 2], h[S - 1]);
+#pragma unroll
+    for (int k = 0; k + 1 < S - ((S & 1) ? 0 : 2); k += 2) qmin = min(qmin, min(h[k], h[k + 1]));
+    return qmin;
+}
+#ifndef NMB_SWEEP_TRIP
+#define NMB_SWEEP_TRIP 4
+#endif
+constexpr int kSweepTrip = NMB_SWEEP_TRIP;  // timestamps per trip of the sweep's inner loop (even, divides the chunk)
+
 template <int S, int THREADS, int CH, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gpb,
@@ -282,33 +302,60 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
             const double* src = (tid & 1 ? lc.w : lc.f) + (long long)cand * lc.npad + base + (tid >> 1) * 16;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
         }
-#pragma unroll 2
-        for (int i = 0; i < CH; ++i) {
-            int qmin = INT_MAX;
-            if (S > 0) {
-                const double ti = tr[i];
+        if (S > 0) {
+            // NT timestamps per trip.  The common case -- none of them can be in transit -- costs, beside the
+            // 2 S DFMA and S / 2 integer minima per timestamp, one more minimum, a compare and a branch per
+            // trip and one DADD per timestamp; the per-timestamp book-keeping runs only on the rare trips that
+            // touch the transit.  Terms are added in timestamp order on both paths.
+            constexpr int NT = kSweepTrip;
+#pragma unroll 1
+            for (int i0 = 0; i0 < CH; i0 += NT) {
+                double tt[NT], mm[NT];
+                int q[NT];
 #pragma unroll
-                for (int k = 0; k + 1 < S; k += 2) {
-                    const double vx0 = fma(vel, ti, ck[k]), vx1 = fma(vel, ti, ck[k + 1]);
-                    qmin = min(qmin, min(__double2hiint(fma(vx0, vx0, b2)), __double2hiint(fma(vx1, vx1, b2))));
+                for (int j = 0; j < NT; j += 2) {
+                    const double2 tv = *reinterpret_cast<const double2*>(tr + i0 + j);
+                    const double2 mv = *reinterpret_cast<const double2*>(tm + i0 + j);
+                    tt[j] = tv.x; tt[j + 1] = tv.y;
+                    mm[j] = mv.x; mm[j + 1] = mv.y;
                 }
-                if (S & 1) {
-                    const double vx = fma(vel, ti, ck[S - 1]);
-                    qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
+                int qall = INT_MAX;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    q[j] = sweep_qmin<S>(vel, tt[j], ck, b2);
+                    qall = min(qall, q[j]);
                 }
-            } else {
+                if (qall > qhi) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) acc += mm[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        if (q[j] > qhi) {
+                            acc += mm[j];
+                        } else {
+                            lo = min(lo, base + i0 + j);
+                            hi = base + i0 + j + 1;
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < CH; ++i) {
+                int qmin = INT_MAX;
                 const double* row = sm.ftab[buf] + i * SP;
                 for (int k = 0; k < Sx; ++k) {
                     const double vx = fma(vel, row[k], nvtc);
                     qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
                 }
-            }
-            const bool hit = qmin <= qhi;
-            const double term = tm[i];
-            if (!hit) acc += term;
-            if (hit) {
-                lo = min(lo, base + i);
-                hi = base + i + 1;
+                const bool hit = qmin <= qhi;
+                const double term = tm[i];
+                if (!hit) acc += term;
+                if (hit) {
+                    lo = min(lo, base + i);
+                    hi = base + i + 1;
+                }
             }
         }
         if ((c + 1) % cpg == 0 || c + 1 == c_end) {  // granule complete: publish its partial sum
