@@ -40,6 +40,9 @@ constexpr int kThreads = 128;  // sweep / window block size
 constexpr int kTPT = 4;        // timestamps per thread in the sweep -> 512-timestamp tiles
 constexpr int kTile = kThreads * kTPT;
 constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-thread sweep
+#ifndef NMB_EVAL_MINB
+#define NMB_EVAL_MINB 5          // resident stage-2 blocks per SM of the default arithmetic (96 registers)
+#endif
 #ifndef NMB_SWEEP_MINB
 #define NMB_SWEEP_MINB 7         // resident 128-walker sweep blocks per SM (72 registers: no spills with four timestamps per trip;
                                  // measured on the 65 k x 4096 sweep: 0.664 ms against 0.692 at 8 blocks and 0.671 at 6)
@@ -262,7 +265,7 @@ int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, d
     // relaxed path: five blocks (20 warps) per SM.  It fits 96 registers with two spilled words, and the shorter
     // per-warp share of the queue outweighs them (measured: -4 % ... -7 % on every workload against four
     // blocks; six blocks spill inside the flux rounds and lose)
-    return launch_eval_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+    return launch_eval_mb<S, NMB_EVAL_MINB, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
 
 // Stage 2 as one launch of queue workers + one direct block per walker (eval_mixed_kernel).
@@ -295,7 +298,7 @@ int launch_mixed(nmb_lc* lc, const double* params, int W, const double* priors, 
                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     if (dtype == NMB_F32) return launch_mixed_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (dtype == NMB_F64_STRICT) return launch_mixed_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
-    return launch_mixed_mb<S, 5, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
+    return launch_mixed_mb<S, NMB_EVAL_MINB, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
 
 // Ensembles between a few hundred walkers and about two resident waves of direct blocks take the mixed

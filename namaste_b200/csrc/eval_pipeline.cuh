@@ -924,7 +924,6 @@ direct_eval_tail(DirectSmem<THREADS>& sm, const LcView& lc, const EvalWs& ws, co
         for (int j = lane; j < nsamp; j += 32) {
             const int h = j / Sx, k = j - h * Sx;
             scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + t0 + h), __ldg(goff + k), wc, cf, &wc.q);
-            if (ws.trace && j == lane && lane == 0) trace_max(ws, 6);  // first flux round of a direct pass done
         }
         __syncwarp();
         if (lane == 0) trace_max(ws, 14);  // flux rounds of a direct pass done
