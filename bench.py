@@ -474,7 +474,7 @@ def measure_lnprob(b, wl, staged, steps, warmup, with_clocks=False, variants=Tru
     fin = np.isfinite(ref_out) & (np.abs(ref_out) < 1e15)
     if variants:
         short = max(3, min(steps, 10))
-        for key, dtype, mode in (("fp32", "f32", "windowed"), ("strict", "strict", "brute")):
+        for key, dtype, mode in (("fp32", "f32", "windowed"), ("fp32_pure", "f32_pure", "windowed"), ("strict", "strict", "brute")):
             b.device_loop(ev(mode, dtype), 3)
             msv, _, _ = b.device_loop(ev(mode, dtype), short)
             vout = out.cpu().numpy().copy()
@@ -724,7 +724,7 @@ def run_ours(args):
         "gpu_launches": int(head["launches"]),
         "mcmc": mcmc,
         "windowed": dict(head["windowed"], e2e=head["e2e_windowed"]["value"]),
-        "fp32": head.get("fp32"), "strict": head.get("strict"),
+        "fp32": head.get("fp32"), "fp32_pure": head.get("fp32_pure"), "strict": head.get("strict"),
         "roofline": roofline_of(b, wl, head, peak_tf, traffic),
         "parity": {"likelihood": "pinned (oracle bitwise vs the reference's own NumPy code; 3 logged known answers)",
                    "sampler": "unpinned (emcee absent: stretch move restated from the publication)",

@@ -57,7 +57,8 @@ extern "C" {
 /* arithmetic type of the transit model */
 #define NMB_F64 64        /* FP64, contracted multiply-adds and <= 1.5-ulp quotients / roots in the two hot cases   */
 #define NMB_F64_STRICT 66 /* FP64 in the reference's own rounding sequence (most elements bit-identical to NumPy) */
-#define NMB_F32 32        /* FP32 occultation (depth space), FP64 geometry and sums; reported separately          */
+#define NMB_F32 32        /* FP32 where 1e-5 on lnprob allows (geometry root, case selection), FP64 for K, E, Pi, lambda_d */
+#define NMB_F32_PURE 33   /* the two hot occultation cases entirely in FP32: 1e-5 ... 1e-4 on lnprob, reported only   */
 
 #define NMB_NPAR 6       /* tcen, b, vel, RpRs, LD1, LD2  (namaste.py:1153)                */
 #define NMB_PRIOR_COLS 6 /* lo, hi, kind(0 none,1 gaussian,2 normlim,3 evans), mu, sigma, pad */

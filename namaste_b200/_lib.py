@@ -13,7 +13,7 @@ if os.environ.get("NMB_LIB"):  # diagnostics: A/B builds of the same library
 
 NMB_OK, NMB_ERR_ARG, NMB_ERR_CUDA, NMB_ERR_PRECOND, NMB_ERR_NAN = 0, -1, -2, -3, -4
 MODE_BRUTE, MODE_WINDOWED, MODE_FUSED = 0, 1, 2
-F64, F32, F64_STRICT = 64, 32, 66
+F64, F32, F64_STRICT, F32_PURE = 64, 32, 66, 33
 MODES = {"brute": MODE_BRUTE, "windowed": MODE_WINDOWED, "fused": MODE_FUSED,
          MODE_BRUTE: MODE_BRUTE, MODE_WINDOWED: MODE_WINDOWED, MODE_FUSED: MODE_FUSED}
 

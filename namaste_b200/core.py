@@ -7,10 +7,11 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import MODES, F64, F32, F64_STRICT, as_f64, check, load, ptr
+from ._lib import MODES, F64, F32, F64_STRICT, F32_PURE, as_f64, check, load, ptr
 
 DTYPES = {"f64": F64, "f32": F32, F64: F64, F32: F32, "float64": F64, "float32": F32,
-          "f64_strict": F64_STRICT, "strict": F64_STRICT, F64_STRICT: F64_STRICT}
+          "f64_strict": F64_STRICT, "strict": F64_STRICT, F64_STRICT: F64_STRICT,
+          "f32_pure": F32_PURE, F32_PURE: F32_PURE}
 
 PARAM_NAMES = ("tcen", "b", "vel", "RpRs", "LD1", "LD2")  # namaste/namaste.py:1153
 _PRIOR_KINDS = {"gaussian": 1.0, "normlim": 2.0, "evans": 3.0}

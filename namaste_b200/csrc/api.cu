@@ -198,9 +198,10 @@ static int lnprob_impl(nmb_lc* lc, const double* params, int64_t W, const double
                        double* loglike, int mode, int dtype, void* stream, const nmb::SampleCtx& sc) {
     if (!lc || !params || (!lnprob && !sc.enabled)) return fail(NMB_ERR_ARG, "nmb_lnprob: null pointer");
     if (W < 1 || W > (1 << 24)) return fail(NMB_ERR_ARG, "nmb_lnprob: W out of range");
-    if (dtype != NMB_F64 && dtype != NMB_F32 && dtype != NMB_F64_STRICT)
-        return fail(NMB_ERR_ARG, "nmb_lnprob: dtype must be NMB_F64, NMB_F64_STRICT or NMB_F32");
-    if (dtype == NMB_F32 && mode == NMB_MODE_FUSED) return fail(NMB_ERR_ARG, "nmb_lnprob: NMB_MODE_FUSED is FP64 only");
+    if (dtype != NMB_F64 && dtype != NMB_F32 && dtype != NMB_F64_STRICT && dtype != NMB_F32_PURE)
+        return fail(NMB_ERR_ARG, "nmb_lnprob: dtype must be NMB_F64, NMB_F64_STRICT, NMB_F32 or NMB_F32_PURE");
+    if ((dtype == NMB_F32 || dtype == NMB_F32_PURE) && mode == NMB_MODE_FUSED)
+        return fail(NMB_ERR_ARG, "nmb_lnprob: NMB_MODE_FUSED is FP64 only");
     cudaStream_t st = (cudaStream_t)stream;
     std::lock_guard<std::recursive_mutex> lock(lc->mu);
     if (int rc0 = lc->order_on(st)) return rc0;

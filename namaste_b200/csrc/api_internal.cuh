@@ -260,7 +260,8 @@ int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors
 template <int S>
 int launch_eval(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                 cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
-    if (dtype == NMB_F32) return launch_eval_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (dtype == NMB_F32) return launch_eval_mb<S, 5, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (dtype == NMB_F32_PURE) return launch_eval_mb<S, 4, 4>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (dtype == NMB_F64_STRICT) return launch_eval_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
     // relaxed path: five blocks (20 warps) per SM.  It fits 96 registers with two spilled words, and the shorter
     // per-warp share of the queue outweighs them (measured: -4 % ... -7 % on every workload against four
@@ -296,7 +297,7 @@ int launch_mixed_mb(nmb_lc* lc, const double* params, int W, const double* prior
 template <int S>
 int launch_mixed(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
-    if (dtype == NMB_F32) return launch_mixed_mb<S, 4, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
+    if (dtype == NMB_F32) return launch_mixed_mb<S, 5, 2>(lc, params, W, priors, lnprob, loglike, st, sc);
     if (dtype == NMB_F64_STRICT) return launch_mixed_mb<S, 4, 1>(lc, params, W, priors, lnprob, loglike, st, sc);
     return launch_mixed_mb<S, NMB_EVAL_MINB, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
@@ -365,7 +366,7 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
                  cudaStream_t st, const nmb::SampleCtx& sc, int dtype) {
     const size_t CW = (size_t)lc->ncand * W;
     if (int rc = ensure_ws(lc, CW, lc->ngran, st)) return rc;
-    const bool mixed = use_mixed(lc, CW);
+    const bool mixed = use_mixed(lc, CW) && dtype != NMB_F32_PURE;  // (the pure-FP32 variant exists on the queue path only)
     lc->ws.direct_cap = mixed ? direct_cap_slots(lc, true) : 0;
     lc->timer.mark(0, st);
     // 128-walker blocks when they alone fill the GPU, single-warp blocks (finer spread) otherwise
@@ -438,13 +439,13 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
     // and in the GP model mode, the thread-per-walker kernel fills the queue for eval_slots_kernel
     bool direct = false;
     lc->ws.direct_cap = direct_cap_slots(lc, false);  // read by window_direct_kernel only (it never calls push_slots)
-    if (!lc->ws.modelbuf) {
+    if (!lc->ws.modelbuf && dtype != NMB_F32_PURE) {
         int rc = dtype == NMB_F32          ? launch_direct<S, 2>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
                  : dtype == NMB_F64_STRICT ? launch_direct<S, 1>(lc, params, W, priors, lnprob, loglike, st, sc, &direct)
                                            : launch_direct<S, 3>(lc, params, W, priors, lnprob, loglike, st, sc, &direct);
         if (rc) return rc;
     }
-    const bool mixed = !direct && use_mixed(lc, CW);
+    const bool mixed = !direct && use_mixed(lc, CW) && dtype != NMB_F32_PURE;
     if (!direct) {
         lc->ws.direct_cap = mixed ? direct_cap_slots(lc, true) : 0;
         CU(launch_pdl(nmb::window_ranges_kernel<kWinThreads>, dim3((unsigned)((CW + kWinThreads - 1) / kWinThreads)),

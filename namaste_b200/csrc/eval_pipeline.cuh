@@ -575,7 +575,8 @@ constexpr int kEvalPass = NMB_EVALPASS;  // supersamples of one slot (the unit o
 constexpr int kEvalMerge = NMB_EVALMERGE;  // most consecutive slots of a walker a warp evaluates in one pass
 
 // PATH: 0 = general IEEE FP64, 1 = FP64 hot path in the reference's rounding sequence (NMB_F64_STRICT),
-//       2 = FP32 hot path (NMB_F32), 3 = relaxed FP64 hot path (NMB_F64, the default)
+//       2 = FP32 geometry + FP64 occultation (NMB_F32), 3 = relaxed FP64 hot path (NMB_F64, the default),
+//       4 = FP32 occultation (NMB_F32_PURE; queue path only)
 template <int PATH>
 __device__ __forceinline__ double sample_flux_eval(double ti, double offk, const WalkerConsts& wc,
                                                    const QuadConstsF& cf, const QuadConsts* gq);
@@ -625,8 +626,31 @@ __device__ __forceinline__ double sample_flux_eval<0>(double ti, double offk, co
                                                       const QuadConstsF&, const QuadConsts*) {
     return sample_flux(ti, offk, wc);
 }
+// NMB_F32: FP32 where the 1e-5 tolerance on lnprob allows it -- the geometry's square root and with it the case a
+// sample falls in -- and FP64 (the relaxed arithmetic of the default) where it does not: K, E, Pi and their
+// combination lambda_d lose a factor ~60 to cancellation, and the limb's acos / sqrt amplify argument rounding by
+// 1 / sqrt(distance to contact).  The occultation is the FP64 function evaluated at the float-rounded z
+// (|dz| <= 3e-8 z, |dF| <= 1e-8).  lnprob stays within ~1e-7 of the FP64 result on every fixture.
 template <>
 __device__ __forceinline__ double sample_flux_eval<2>(double ti, double offk, const WalkerConsts& wc,
+                                                      const QuadConstsF&, const QuadConsts* gq) {
+    const double ft = ti + offk;
+    const double x = ft - wc.tcen;          // FP64 difference of the absolute times (FP32 here costs 2e-4 on ll)
+    const double vx = wc.vel * x;
+    const double q = fma(vx, vx, wc.b2);
+    const double z = (double)sqrtf((float)q);
+    if (z > wc.q.onep) return wc.q.fout;
+    double F;
+    if (!occultquad_relaxed(z, wc.q, F) || !(fabs(F) <= 1e300)) {
+        const double zz = ::sqrt(q);
+        F = (zz > wc.q.onep) ? wc.q.fout : sample_flux_slowpath(zz, gq);
+    }
+    return F;
+}
+// NMB_F32_PURE: the two hot cases entirely in FP32 (depth space).  Reported with its error: 1e-5 ... 1e-4 on
+// lnprob, because FP32 rounding of K, E and Pi (1e-7 each) is amplified ~60x by the cancellation in lambda_d.
+template <>
+__device__ __forceinline__ double sample_flux_eval<4>(double ti, double offk, const WalkerConsts& wc,
                                                       const QuadConstsF& cf, const QuadConsts* gq) {
     const double ft = ti + offk;
     const double x = ft - wc.tcen;          // FP64 difference of the absolute times, then FP32
@@ -761,7 +785,7 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, cons
                 for (int i = lane; i < (int)(sizeof(WalkerConsts) / 8); i += 32) dst[i] = __ldcg(src + i);
                 __syncwarp();
             }
-            if (PATH == 2) cf = to_f32(wc.q);
+            if (PATH == 4) cf = to_f32(wc.q);
             gt = lc.t + (long long)cand * lc.npad;
             gf = lc.f + (long long)cand * lc.npad;
             gw_ = lc.w + (long long)cand * lc.npad;
@@ -905,7 +929,7 @@ direct_eval_tail(DirectSmem<THREADS>& sm, const LcView& lc, const EvalWs& ws, co
     const int TSW = ws.tsw;
     WalkerConsts& wc = sm.wc[warp];
     QuadConstsF cf = QuadConstsF{};
-    if (PATH == 2) cf = to_f32(wc.q);
+    if (PATH == 4) cf = to_f32(wc.q);
     const int per = (nsl + NWARP - 1) / NWARP;
     const int s0 = warp * per, s1 = min(nsl, s0 + per);
     if (s0 < s1) {

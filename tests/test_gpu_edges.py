@@ -86,13 +86,35 @@ def _workload(name):
     return bench.make_workload(name)
 
 
-@pytest.mark.parametrize("name,nspot", [("k2", 6), ("kepler", 2)])
-def test_full_size_properties(nb, name, nspot):
-    """BASELINE configs 2 (N=4000, S=11, W=1024) and 3 (N=65000, S=15, W=4096) at full size."""
+def _special_walkers(wl, rng, n_random):
+    """Walkers that exercise every branch of the path at full size: uniform in the prior box, from the tight
+    ball, slow (vel ~ 0: nearly every timestamp in transit), grazing (b ~ 1 + p), a large planet (p > 1/2,
+    outside the hot cases), a planet over the disc centre for a long time (b ~ 0), and outside the soft walls."""
+    th = wl["theta"] if "theta" in wl else wl["pos"][-1]
+    tab = wl["priors"] if wl["priors"].ndim == 2 else wl["priors"][0]
+    box = tab[:, 0] + (tab[:, 1] - tab[:, 0]) * rng.uniform(0, 1, (n_random, 6))
+    ball = th[None, :] * (1 + 1e-3 * rng.standard_normal((4, 6)))
+    special = np.repeat(th[None, :], 6, axis=0)
+    special[0, 2] = 1e-4                       # vel ~ 0: z ~ b for every sample of the light curve
+    special[1, 1] = 1.0 + 0.999 * th[3]        # grazing: only the limb case, shallow
+    special[2, 3] = 0.62                       # p > 1/2: the general path (cases i02 / i08 / i09 with a large planet)
+    special[3, 1] = 1e-3                       # central transit: case i09 around mid-transit
+    special[4, 0] = th[0] + 40.0; special[4, 3] = 0.3   # beyond the tcen and RpRs walls: soft-wall terms of 1e20
+    special[5, 2] = 0.05 * th[2]; special[5, 1] = 0.9   # slow and nearly grazing: a long limb-dominated range
+    return np.vstack([box, ball, special])
+
+
+@pytest.mark.parametrize("name,nbox", [("k2", 6), ("kepler", 6), ("tess", 6)])
+def test_full_size_properties(nb, name, nbox):
+    """BASELINE configs 2 (N=4000, S=11, W=1024), 3 (N=65000, S=15, W=4096) and one GPU's share of 5 (N=500000,
+    S=10, W=2048) at full size: properties that need no oracle on every walker, plus 16 oracle spot checks that
+    cover the prior box, the tight ball and the special walkers of `_special_walkers`."""
     from oracle import namaste_oracle as o
     wl = _workload(name)
     staged = nb.LightCurve(wl["lc"], oversamp=wl["S"])
-    pos, tab = wl["pos"], wl["priors"]
+    pos, tab = wl["pos"].copy(), wl["priors"]
+    spot = _special_walkers(wl, np.random.default_rng(77), nbox)
+    pos[-len(spot):] = spot                         # the last 16 walkers of the ensemble are the spot checks
     brute = staged.lnprob(pos, tab, mode="brute")
     win = staged.lnprob(pos, tab, mode="windowed")
     assert brute.shape == (wl["W"],) and np.isfinite(brute).all()
@@ -104,11 +126,46 @@ def test_full_size_properties(nb, name, nspot):
     assert np.array_equal(staged.lnprob(pos[perm], tab, mode="windowed"), win[perm])
     # idempotence: evaluating again gives the same bits (workspace left clean)
     assert np.array_equal(staged.lnprob(pos, tab, mode="brute"), brute)
-    # oracle spot checks: the first walkers (uniform in the prior box) and one from the tight ball
     pri = priors_from_table(tab)
-    for i in list(range(nspot)) + [wl["W"] - 1]:
-        ref = o.mono_only_logprob(pos[i], wl["lc"], pri, wl["S"])
-        assert abs(brute[i] - ref) <= 1e-10 * abs(ref) and abs(win[i] - ref) <= 1e-10 * abs(ref), i
+    idx = list(range(wl["W"] - len(spot), wl["W"]))
+    assert len(idx) >= 16
+    with np.errstate(all="ignore"):
+        for i in idx:
+            ref = o.mono_only_logprob(pos[i], wl["lc"], pri, wl["S"])
+            assert abs(brute[i] - ref) <= 1e-10 * abs(ref) and abs(win[i] - ref) <= 1e-10 * abs(ref), (name, i, brute[i], win[i], ref)
+    staged.close()
+
+
+def test_candidate_batch_256_distinct_light_curves(nb):
+    """One GPU's share of BASELINE config 4: 256 candidates with their own light curves, transits, priors and
+    100-walker ensembles, staged and evaluated as one batch.  Oracle spot checks on 48 (candidate, walker)
+    pairs, and every candidate of a sample evaluated on its own gives the bits it has inside the batch."""
+    from oracle import namaste_oracle as o
+    sys.path.insert(0, ROOT)
+    import bench
+    wl = bench.make_batch(0)
+    rng = np.random.default_rng(5)
+    pos = wl["pos"].copy()
+    # some prior-box walkers in every candidate (the bench ensemble is a tight ball only)
+    for c in range(wl["C"]):
+        tab = wl["priors"][c]
+        pos[c, :4] = tab[:, 0] + (tab[:, 1] - tab[:, 0]) * rng.uniform(0, 1, (4, 6))
+    staged = nb.LightCurve(wl["curves"], oversamp=wl["S"])
+    res = {mode: staged.lnprob(pos, wl["priors"], mode=mode) for mode in ("brute", "windowed")}
+    assert res["brute"].shape == (256, 100) and np.isfinite(res["brute"]).all()
+    assert rel(res["brute"], res["windowed"]).max() < 1e-12
+    pairs = [(int(c), int(w)) for c, w in zip(rng.integers(0, 256, 48), rng.integers(0, 100, 48))]
+    pairs[:8] = [(c, w % 4) for c, w in pairs[:8]]          # prior-box walkers among them
+    with np.errstate(all="ignore"):
+        for c, w in pairs:
+            ref = o.mono_only_logprob(pos[c, w], wl["curves"][c], priors_from_table(wl["priors"][c]), wl["S"])
+            for mode in ("brute", "windowed"):
+                assert abs(res[mode][c, w] - ref) <= 1e-10 * abs(ref), (mode, c, w)
+    for c in (0, 37, 255):
+        single = nb.LightCurve(wl["curves"][c], oversamp=wl["S"])
+        for mode in ("brute", "windowed"):
+            assert np.array_equal(single.lnprob(pos[c], wl["priors"][c], mode=mode), res[mode][c]), (mode, c)
+        single.close()
     staged.close()
 
 
