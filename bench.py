@@ -632,6 +632,51 @@ def cpu_config1_mcmc(wl, nsteps=6):
             "kind": "port", "note": "NumPy oracle lnprob + CPU stretch move (emcee restated), process pool over walkers"}
 
 
+def _oracle_flatten(lc):
+    from oracle import flatten_oracle as fo
+    return fo.reduce_noise(lc, winsize=4.5, stepsize=0.125)[:, 1]
+
+
+def measure_detrend(b, ncand=256, reps=3):
+    """The pre-fit row for one GPU's share of BASELINE configs[3]: AnomCutDiff(3.75) and two passes of
+    ReduceNoise(winsize=4.5, stepsize=0.125) (namaste.py:1109, :1143; Example.ipynb cell 45) over 256 light curves of
+    4000 points in batched device calls, host arrays in and out; the reference's CPU ReduceNoise (NumPy port, process
+    pool) beside it on a sample of the same light curves."""
+    from namaste_b200 import k2flatten
+    wl = make_batch(0, ncand=ncand)
+    rng = np.random.default_rng(11)
+    curves = []
+    for lc in wl["curves"]:
+        c = lc.copy()
+        x = (c[:, 0] - c[0, 0]) / 80.0
+        c[:, 1] *= 1.0 + 2e-3 * np.sin(2 * np.pi * (x * rng.uniform(3, 9) + rng.uniform())) + 1e-3 * x   # slow systematics
+        curves.append(c)
+    def run():
+        keep = k2flatten.AnomCutDiffBatch([c[:, 1] for c in curves], 3.75)
+        cut = [c[k] for c, k in zip(curves, keep)]
+        flat = k2flatten.ReduceNoiseBatch(cut, winsize=4.5, stepsize=0.125)
+        return k2flatten.ReduceNoiseBatch(flat, winsize=4.5, stepsize=0.125)
+    run()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        flat2 = run()
+    dt = (time.perf_counter() - t0) / reps
+    out = {"candidates": ncand, "points_each": wl["N"], "ms_per_batch": 1e3 * dt, "light_curves_per_s": ncand / dt,
+           "passes": "AnomCutDiff(3.75) + ReduceNoise(4.5, 0.125) twice", "note": "host arrays in and out, device buffers kept in one workspace"}
+    if b.rank == 0 and not b.args.no_cpu:
+        import multiprocessing as mp
+        cores = len(os.sched_getaffinity(0))
+        sample = curves[:cores]
+        pool = mp.Pool(cores)
+        t0 = time.perf_counter()
+        ref = pool.map(_oracle_flatten, sample)       # one ReduceNoise pass per light curve
+        dtc = time.perf_counter() - t0
+        pool.close()
+        out["cpu_baseline"] = {"light_curves_per_s": len(sample) / dtc / 2.0, "cores": cores, "kind": "port",
+                               "sample": "%d light curves, one ReduceNoise pass each in %.1f s (rate halved for the two passes)" % (len(sample), dtc)}
+    return out
+
+
 def run_ours(args):
     b = Bench(args)
     torch, dist, nb = b.torch, b.dist, b.nb
@@ -687,6 +732,7 @@ def run_ours(args):
                                     "kernels": list(rb["kernels"]), "stage_ms": list(rb["stage_ms"]),
                                     "note": "one GPU's share of BASELINE configs[3]; the headline of the N > 1 lines"}
         stb.close()
+        extra["detrend"] = measure_detrend(b)
 
     if rank != 0:
         if world > 1:

@@ -175,13 +175,28 @@ int nmb_gp_lnprob(nmb_lc* lc, const double* params, int64_t W, int kind, const d
 int nmb_gp_lnprob_host(nmb_lc* lc, const double* params, int64_t W, int kind, const double* kfixed, int freemask,
                        const double* priors, double* lnprob, double* loglike);
 
-/* ---- detrending: k2flatten.ReduceNoise (namaste/k2flatten.py:51-84; dopolyfit :5-17) ------------------
- * One thread block per detrending step runs the clipped weighted polynomial fit of the step's window
- * and writes f - p(t) + 1 for the box points the step owns.  Host arrays: t (shifted to start at 0),
- * f and e (divided by the median flux) of length n; steps [nsteps][6] = wlo, blo, bhi, whi (window =
- * [wlo, blo) U [bhi, whi), box = [blo, bhi)) and olo, ohi (owned part of the box); out [n] in/out. */
-int nmb_flatten(const double* t, const double* f, const double* e, int64_t n, const int32_t* steps, int64_t nsteps,
-                double winsize, int deg, int niter, double sigclip, double* out);
+/* ---- the pre-fit steps for a batch of candidates -----------------------------------------------
+ * Namaste prepares every light curve with an outlier cut, two detrending passes and a window around the transit
+ * before it fits (namaste/namaste.py:1109, :1143 / Example.ipynb cell 45, :550-556).  One workspace handle owns the
+ * device buffers (grown on demand, kept between calls) and a stream; host arrays are [ncand][stride], candidate c
+ * holding n[c] valid points.
+ *   nmb_anomcut_batch     <- AnomCutDiff(flux, thresh)                       (namaste/namaste.py:1459-1467)
+ *                            keep [ncand][stride] out, 1 = keep; flux must be NaN-free (nonan, :1456)
+ *   nmb_flatten_batch     <- k2flatten.ReduceNoise(lc, winsize, stepsize, polydegree, niter, sigmaclip, gapthreshold)
+ *                            (namaste/k2flatten.py:51-84; formwindow :19-40, dopolyfit :5-17): t shifted to start at 0,
+ *                            f and e divided by the median flux; out = detrended flux, 0 where no step owns a point
+ *   nmb_window_mask_batch <- the fit window of RunMCMC (namaste/namaste.py:550-556): keep = abs(t - tcen < width)
+ *                            (the reference's one-sided quirk) or, two_sided != 0, |t - tcen| < width          */
+typedef struct nmb_flat nmb_flat;
+int nmb_flat_create(nmb_flat** out);
+void nmb_flat_destroy(nmb_flat* w);
+int nmb_anomcut_batch(nmb_flat* w, const double* flux, const int64_t* n, int64_t ncand, int64_t stride, double thresh,
+                      uint8_t* keep);
+int nmb_flatten_batch(nmb_flat* w, const double* t, const double* f, const double* e, const int64_t* n, int64_t ncand,
+                      int64_t stride, double winsize, double stepsize, double gapthreshold, int deg, int niter,
+                      double sigclip, double* out);
+int nmb_window_mask_batch(nmb_flat* w, const double* t, const int64_t* n, int64_t ncand, int64_t stride,
+                          const double* tcen, const double* width, int two_sided, uint8_t* keep);
 
 /* ---- measurement helpers (used by bench.py) ------------------------------------------------ */
 /* Sustained DFMA throughput of this GPU in TFLOP/s (2 flops per DFMA), CUDA-event timed. */

@@ -64,8 +64,12 @@ SIGNATURES = {
                                            ctypes.POINTER(ctypes.c_int64)]),
     "nmb_sampler_devptr": (_vp, [_vp, ctypes.c_int]),
     "nmb_sampler_stream": (_vp, [_vp]),
-    "nmb_flatten": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
-                                   ctypes.c_int, ctypes.c_double, _vp]),
+    "nmb_flat_create": (ctypes.c_int, [ctypes.POINTER(_vp)]),
+    "nmb_flat_destroy": (None, [_vp]),
+    "nmb_anomcut_batch": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, _vp]),
+    "nmb_flatten_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                         ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double, _vp]),
+    "nmb_window_mask_batch": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int64, _vp, _vp, ctypes.c_int, _vp]),
     "nmb_measure_fp64_peak": (ctypes.c_int, [_c_double_p, _c_double_p]),
     "nmb_debug_trace": (ctypes.c_int, [_vp, _vp]),
     "nmb_last_kernels": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p)]),

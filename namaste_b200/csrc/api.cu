@@ -429,67 +429,185 @@ extern "C" int nmb_stage_times(nmb_lc* lc, double* stage1_ms, double* stage2_ms,
     return NMB_OK;
 }
 
-// ---- detrending (namaste/k2flatten.py ReduceNoise) ------------------------------------------------
-// t (already shifted to start at 0), f, e (already divided by the median flux): host arrays [n];
-// steps: host array [nsteps] of {wlo, blo, bhi, whi, olo, ohi} index sextets; out: host [n], entries
-// outside every owned range are left untouched.
-extern "C" int nmb_flatten(const double* t, const double* f, const double* e, int64_t n, const int32_t* steps,
-                           int64_t nsteps, double winsize, int deg, int niter, double sigclip, double* out) {
-    if (!t || !f || !e || !steps || !out) return fail(NMB_ERR_ARG, "nmb_flatten: null pointer");
-    if (n < 1 || nsteps < 1) return fail(NMB_ERR_ARG, "nmb_flatten: empty input");
-    if (deg < 0 || deg > nmb::kFlatMaxDeg) return fail(NMB_ERR_ARG, "nmb_flatten: polynomial degree must be in 0..5");
-    if (niter < 0) return fail(NMB_ERR_ARG, "nmb_flatten: niter < 0");
-    std::vector<nmb::FlatStep> hs(nsteps);
-    int maxwin = 1;
-    for (int64_t s = 0; s < nsteps; ++s) {
-        const int32_t* r = steps + 6 * s;
-        nmb::FlatStep& st = hs[s];
-        st.wlo = r[0]; st.blo = r[1]; st.bhi = r[2]; st.whi = r[3]; st.olo = r[4]; st.ohi = r[5];
-        if (st.wlo < 0 || st.whi > n || st.blo < 0 || st.bhi > n || st.blo > st.bhi || st.olo < st.blo || st.ohi > st.bhi)
-            return fail(NMB_ERR_ARG, "nmb_flatten: step indices out of range");
-        const int n1 = std::max(0, st.blo - st.wlo), n2 = std::max(0, st.whi - st.bhi);
-        if (n1 + n2 < deg + 1) {
-            char buf[160];
-            snprintf(buf, sizeof buf, "step %lld: the fitting window holds %d points, fewer than the %d a degree-%d polynomial needs",
-                     (long long)s, n1 + n2, deg + 1, deg);
-            return fail(NMB_ERR_PRECOND, buf);
-        }
-        maxwin = std::max(maxwin, n1 + n2);
-        // abscissa scaling: centre and half-width of the window's own time span
-        const double xa = n1 > 0 ? t[st.wlo] : t[st.bhi], xb = n2 > 0 ? t[st.whi - 1] : t[st.blo - 1];
-        st.xc = 0.5 * (xa + xb);
-        st.h = std::max(0.5 * (xb - xa), 1e-12);
-        (void)winsize;
+// ---- the pre-fit steps for a batch of candidates: outlier cut, detrending, fit window ---------------------------
+// (namaste/namaste.py:1459-1467 AnomCutDiff; namaste/k2flatten.py:51-84 ReduceNoise; namaste/namaste.py:550-556)
+// One workspace handle owns the device buffers (grown on demand, never freed between calls) and a stream, so a
+// call costs its copies and launches only.  Host arrays are [ncand][stride], candidate c holding n[c] points.
+struct nmb_flat {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    double *d_t = nullptr, *d_f = nullptr, *d_e = nullptr, *d_out = nullptr, *d_par = nullptr;
+    unsigned char* d_keep = nullptr;
+    long long *d_n = nullptr, *d_off = nullptr;
+    nmb::FlatStep* d_steps = nullptr;
+    int* d_info = nullptr;
+    size_t cap_pts = 0, cap_cand = 0, cap_steps = 0;
+    std::mutex mu;
+};
+
+extern "C" int nmb_flat_create(nmb_flat** out) {
+    if (!out) return fail(NMB_ERR_ARG, "nmb_flat_create: null pointer");
+    nmb_flat* w = new nmb_flat;
+    cudaError_t e = cudaGetDevice(&w->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&w->d_info, 2 * sizeof(int));
+    if (e != cudaSuccess) {
+        delete w;
+        return cuda_fail(e, "nmb_flat_create");
     }
-    const size_t smem = (size_t)maxwin * (5 * sizeof(double) + 1) + 16;
-    if (smem > 200 * 1024) return fail(NMB_ERR_ARG, "nmb_flatten: fitting window too large for shared memory");
-    double *dt = nullptr, *df = nullptr, *de = nullptr, *dout = nullptr;
-    nmb::FlatStep* dsteps = nullptr;
-    auto cleanup = [&]() { cudaFree(dt); cudaFree(df); cudaFree(de); cudaFree(dout); cudaFree(dsteps); };
-    cudaError_t err = cudaSuccess;
-    if ((err = cudaMalloc(&dt, n * sizeof(double))) != cudaSuccess || (err = cudaMalloc(&df, n * sizeof(double))) != cudaSuccess ||
-        (err = cudaMalloc(&de, n * sizeof(double))) != cudaSuccess || (err = cudaMalloc(&dout, n * sizeof(double))) != cudaSuccess ||
-        (err = cudaMalloc(&dsteps, nsteps * sizeof(nmb::FlatStep))) != cudaSuccess ||
-        (err = cudaMemcpy(dt, t, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (err = cudaMemcpy(df, f, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (err = cudaMemcpy(de, e, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (err = cudaMemcpy(dout, out, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (err = cudaMemcpy(dsteps, hs.data(), nsteps * sizeof(nmb::FlatStep), cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(err, "nmb_flatten: staging");
+    *out = w;
+    return NMB_OK;
+}
+
+extern "C" void nmb_flat_destroy(nmb_flat* w) {
+    if (!w) return;
+    if (w->st) cudaStreamSynchronize(w->st);
+    cudaFree(w->d_t); cudaFree(w->d_f); cudaFree(w->d_e); cudaFree(w->d_out); cudaFree(w->d_par); cudaFree(w->d_keep);
+    cudaFree(w->d_n); cudaFree(w->d_off); cudaFree(w->d_steps); cudaFree(w->d_info);
+    if (w->st) cudaStreamDestroy(w->st);
+    delete w;
+}
+
+namespace {
+
+int flat_reserve(nmb_flat* w, size_t pts, size_t ncand, size_t nsteps) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != w->device) return fail(NMB_ERR_ARG, "nmb_flat: the workspace belongs to another CUDA device");
+    if (pts > w->cap_pts) {
+        cudaFree(w->d_t); cudaFree(w->d_f); cudaFree(w->d_e); cudaFree(w->d_out); cudaFree(w->d_keep);
+        w->d_t = w->d_f = w->d_e = w->d_out = nullptr; w->d_keep = nullptr; w->cap_pts = 0;
+        CU(cudaMalloc(&w->d_t, pts * sizeof(double)));
+        CU(cudaMalloc(&w->d_f, pts * sizeof(double)));
+        CU(cudaMalloc(&w->d_e, pts * sizeof(double)));
+        CU(cudaMalloc(&w->d_out, pts * sizeof(double)));
+        CU(cudaMalloc(&w->d_keep, pts));
+        w->cap_pts = pts;
     }
-    if (smem > 48 * 1024 &&
-        (err = cudaFuncSetAttribute(nmb::flatten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(err, "nmb_flatten: shared memory");
+    if (ncand > w->cap_cand) {
+        cudaFree(w->d_n); cudaFree(w->d_off); cudaFree(w->d_par);
+        w->d_n = w->d_off = nullptr; w->d_par = nullptr; w->cap_cand = 0;
+        CU(cudaMalloc(&w->d_n, ncand * sizeof(long long)));
+        CU(cudaMalloc(&w->d_off, (ncand + 1) * sizeof(long long)));
+        CU(cudaMalloc(&w->d_par, 2 * ncand * sizeof(double)));
+        w->cap_cand = ncand;
     }
-    nmb::flatten_kernel<<<(unsigned)nsteps, nmb::kFlatThreads, smem>>>(dt, df, de, dsteps, deg, niter, sigclip, maxwin, dout);
+    if (nsteps > w->cap_steps) {
+        cudaFree(w->d_steps);
+        w->d_steps = nullptr; w->cap_steps = 0;
+        CU(cudaMalloc(&w->d_steps, nsteps * sizeof(nmb::FlatStep)));
+        w->cap_steps = nsteps;
+    }
+    return NMB_OK;
+}
+
+int flat_check_sizes(const int64_t* n, int64_t ncand, int64_t stride, int64_t nmin, const char* who) {
+    if (ncand < 1 || stride < 1) return fail(NMB_ERR_ARG, std::string(who) + ": empty batch");
+    if ((double)ncand * (double)stride > 2.0e9) return fail(NMB_ERR_ARG, std::string(who) + ": batch exceeds 2^31 points");
+    for (int64_t c = 0; c < ncand; ++c)
+        if (n[c] < nmin || n[c] > stride) return fail(NMB_ERR_ARG, std::string(who) + ": a light curve is too short or longer than the stride");
+    return NMB_OK;
+}
+
+}  // namespace
+
+// AnomCutDiff(flux, thresh) for ncand NaN-free flux series; keep [ncand][stride] out (1 = keep)
+extern "C" int nmb_anomcut_batch(nmb_flat* w, const double* flux, const int64_t* n, int64_t ncand, int64_t stride,
+                                 double thresh, uint8_t* keep) {
+    if (!w || !flux || !n || !keep) return fail(NMB_ERR_ARG, "nmb_anomcut_batch: null pointer");
+    if (int rc = flat_check_sizes(n, ncand, stride, 3, "nmb_anomcut_batch")) return rc;
+    std::lock_guard<std::mutex> lock(w->mu);
+    const size_t pts = (size_t)ncand * stride;
+    if (int rc = flat_reserve(w, pts, ncand, 0)) return rc;
+    std::vector<long long> hn(n, n + ncand);
+    CU(cudaMemcpyAsync(w->d_n, hn.data(), ncand * sizeof(long long), cudaMemcpyHostToDevice, w->st));
+    CU(cudaMemcpyAsync(w->d_f, flux, pts * sizeof(double), cudaMemcpyHostToDevice, w->st));
+    nmb::anomcut_kernel<<<(unsigned)ncand, nmb::kCutThreads, 0, w->st>>>(w->d_f, w->d_n, stride, thresh, w->d_keep);
     g_launches++;
-    if ((err = cudaGetLastError()) != cudaSuccess || (err = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(err, "nmb_flatten");
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(keep, w->d_keep, pts, cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    return NMB_OK;
+}
+
+// keep = abs(t - tcen < width) (the reference's one-sided quirk) or |t - tcen| < width, per candidate
+extern "C" int nmb_window_mask_batch(nmb_flat* w, const double* t, const int64_t* n, int64_t ncand, int64_t stride,
+                                     const double* tcen, const double* width, int two_sided, uint8_t* keep) {
+    if (!w || !t || !n || !tcen || !width || !keep) return fail(NMB_ERR_ARG, "nmb_window_mask_batch: null pointer");
+    if (int rc = flat_check_sizes(n, ncand, stride, 1, "nmb_window_mask_batch")) return rc;
+    std::lock_guard<std::mutex> lock(w->mu);
+    const size_t pts = (size_t)ncand * stride;
+    if (int rc = flat_reserve(w, pts, ncand, 0)) return rc;
+    std::vector<long long> hn(n, n + ncand);
+    CU(cudaMemcpyAsync(w->d_n, hn.data(), ncand * sizeof(long long), cudaMemcpyHostToDevice, w->st));
+    CU(cudaMemcpyAsync(w->d_t, t, pts * sizeof(double), cudaMemcpyHostToDevice, w->st));
+    CU(cudaMemcpyAsync(w->d_par, tcen, ncand * sizeof(double), cudaMemcpyHostToDevice, w->st));
+    CU(cudaMemcpyAsync(w->d_par + ncand, width, ncand * sizeof(double), cudaMemcpyHostToDevice, w->st));
+    nmb::window_mask_kernel<<<(unsigned)((pts + 255) / 256), 256, 0, w->st>>>(w->d_t, w->d_n, stride, (int)ncand, w->d_par,
+                                                                              w->d_par + ncand, two_sided, w->d_keep);
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(keep, w->d_keep, pts, cudaMemcpyDeviceToHost, w->st));
+    CU(cudaStreamSynchronize(w->st));
+    return NMB_OK;
+}
+
+// ReduceNoise for ncand light curves: t (already shifted to start at 0), f and e (already divided by the median
+// flux) host [ncand][stride]; out host [ncand][stride], entries no detrending step owns stay 0 like in the reference.
+// Windows, boxes and owned ranges are found on the device (flat_windows_kernel), then one thread block per step
+// runs the clipped polynomial fit (flatten_kernel).
+extern "C" int nmb_flatten_batch(nmb_flat* w, const double* t, const double* f, const double* e, const int64_t* n,
+                                 int64_t ncand, int64_t stride, double winsize, double stepsize, double gapthreshold, int deg,
+                                 int niter, double sigclip, double* out) {
+    if (!w || !t || !f || !e || !n || !out) return fail(NMB_ERR_ARG, "nmb_flatten_batch: null pointer");
+    if (int rc = flat_check_sizes(n, ncand, stride, 2, "nmb_flatten_batch")) return rc;
+    if (deg < 0 || deg > nmb::kFlatMaxDeg) return fail(NMB_ERR_ARG, "nmb_flatten_batch: polynomial degree must be in 0..5");
+    if (niter < 0) return fail(NMB_ERR_ARG, "nmb_flatten_batch: niter < 0");
+    if (!(winsize > 0.0) || !(stepsize > 0.0)) return fail(NMB_ERR_ARG, "nmb_flatten_batch: winsize and stepsize must be positive");
+    std::lock_guard<std::mutex> lock(w->mu);
+    // steps of each candidate: nsteps = ceil(lenlc / stepsize)   (k2flatten.py:65)
+    std::vector<long long> off(ncand + 1, 0), hn(n, n + ncand);
+    for (int64_t c = 0; c < ncand; ++c) {
+        const double lenlc = t[c * stride + n[c] - 1];
+        if (!(lenlc > 0.0) || !std::isfinite(lenlc)) return fail(NMB_ERR_ARG, "nmb_flatten_batch: times must start at 0 and increase");
+        off[c + 1] = off[c] + (long long)std::ceil(lenlc / stepsize);
     }
-    cleanup();
+    const long long total = off[ncand];
+    if (total < 1 || total > 0x7fffffffLL) return fail(NMB_ERR_ARG, "nmb_flatten_batch: number of detrending steps out of range");
+    const size_t pts = (size_t)ncand * stride;
+    if (int rc = flat_reserve(w, pts, ncand, (size_t)total)) return rc;
+    cudaStream_t st = w->st;
+    CU(cudaMemcpyAsync(w->d_n, hn.data(), ncand * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w->d_off, off.data(), (ncand + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w->d_t, t, pts * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w->d_f, f, pts * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w->d_e, e, pts * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(w->d_out, 0, pts * sizeof(double), st));
+    CU(cudaMemsetAsync(w->d_info, 0, 2 * sizeof(int), st));
+    nmb::flat_windows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(w->d_t, w->d_n, stride, (int)ncand, w->d_off, winsize,
+                                                                            stepsize, gapthreshold, deg, w->d_steps, w->d_info);
+    g_launches++;
+    CU(cudaGetLastError());
+    int info[2] = {0, 0};
+    CU(cudaMemcpyAsync(info, w->d_info, sizeof info, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (info[1]) {
+        const long long g = info[1] - 1;
+        const int64_t c = std::upper_bound(off.begin(), off.end(), g) - off.begin() - 1;
+        char buf[200];
+        snprintf(buf, sizeof buf, "light curve %lld, step %lld: the fitting window holds fewer than the %d points a degree-%d "
+                 "polynomial needs", (long long)c, (long long)(g - off[c]), deg + 1, deg);
+        return fail(NMB_ERR_PRECOND, buf);
+    }
+    const int maxwin = std::max(1, info[0]);
+    const size_t smem = (size_t)maxwin * (5 * sizeof(double) + 1) + 16;
+    if (smem > 200 * 1024) return fail(NMB_ERR_ARG, "nmb_flatten_batch: fitting window too large for shared memory");
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(nmb::flatten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nmb::flatten_kernel<<<(unsigned)total, nmb::kFlatThreads, smem, st>>>(w->d_t, w->d_f, w->d_e, w->d_steps, deg, niter, sigclip,
+                                                                         maxwin, w->d_out);
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, w->d_out, pts * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return NMB_OK;
 }
 

@@ -152,7 +152,8 @@ class SplitEnsembleSampler(object):
         import torch.distributed as dist
         lib = load()
         if pos0 is not None:
-            check(lib.nmb_sampler_set_state(self._h, ptr(as_f64(pos0)), None), "run_mcmc")
+            p0 = as_f64(pos0)       # keep the (possibly converted) array alive across the call
+            check(lib.nmb_sampler_set_state(self._h, ptr(p0), None), "run_mcmc")
         sp = self.split
         if self.transport in ("local", "p2p"):
             check(lib.nmb_sampler_run_split(self._h, int(nsteps), 1 if storechain else 0), "run_mcmc")

@@ -286,7 +286,8 @@ def _gp_eval(params, lc, priors, gp, want_loglike=False):
     tab = core.prior_table(priors, npar=ndim)
     out = np.empty(len(p))
     ll = np.empty(len(p)) if want_loglike else None
-    check(load().nmb_gp_lnprob_host(staged._h, ptr(p), len(p), kind, ptr(as_f64(kfull)), mask, ptr(tab), ptr(out), ptr(ll)),
+    kf = as_f64(kfull)          # keep the converted array alive across the call
+    check(load().nmb_gp_lnprob_host(staged._h, ptr(p), len(p), kind, ptr(kf), mask, ptr(tab), ptr(out), ptr(ll)),
           "MonoLogProb")
     return out, ll
 

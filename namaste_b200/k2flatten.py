@@ -1,9 +1,12 @@
-"""``k2flatten.ReduceNoise`` on the GPU (namaste/k2flatten.py:51-84; windows :19-40, fit :5-17).
+"""``k2flatten.ReduceNoise`` on the GPU (namaste/k2flatten.py:51-84; windows :19-40, fit :5-17), for one light curve
+or a batch of candidates.
 
-Namaste detrends every light curve with it before fitting (namaste.py:442, Example.ipynb cell 45:
-``ReduceNoise(lc, winsize=4.5, stepsize=0.125)``).  The window bookkeeping (a handful of
-``searchsorted`` calls per step) stays on the host; the clipped polynomial fits -- one per step, 21
-weighted least-squares solves each -- run one thread block per step in csrc/flatten_kernels.cuh.
+Namaste detrends every light curve with it before fitting (namaste.py:1143, Example.ipynb cell 45:
+``ReduceNoise(lc, winsize=4.5, stepsize=0.125)``, twice).  Everything per point and per step runs on the device:
+the window / box bookkeeping of ``formwindow`` (one thread per detrending step) and the clipped polynomial fits
+(one thread block per step, 21 weighted least-squares solves each) -- csrc/flatten_kernels.cuh.  The host only
+shifts the times, divides by the median flux (one ``np.median`` per light curve, as the reference does once per
+star) and pads ragged candidates.  The device buffers live in one workspace handle that is kept between calls.
 """
 import ctypes
 
@@ -11,50 +14,68 @@ import numpy as np
 
 from ._lib import as_f64, check, load, ptr
 
-__all__ = ["ReduceNoise", "step_windows"]
+__all__ = ["ReduceNoise", "ReduceNoiseBatch", "AnomCutDiffBatch", "window_mask_batch", "Workspace"]
 
 
-def step_windows(t, winsize, stepsize, gapthreshold):
-    """Per detrending step: window = [wlo, blo) U [bhi, whi) and box = [blo, bhi) as index ranges into
-    the (zero-based) time array, following formwindow (k2flatten.py:19-40): the window is winsize wide
-    around the step centre; if it runs into a gap wider than gapthreshold on one side only it is
-    shifted to start (or end) at the gap, keeping its width."""
-    n = len(t)
-    lenlc = t[-1]
-    nsteps = int(np.ceil(lenlc / stepsize))
-    cents = np.arange(nsteps) / float(nsteps) * lenlc + stepsize / 2.
-    rows = np.empty((nsteps, 4), dtype=np.int64)
-    for s, cent in enumerate(cents):
-        lo_edge, hi_edge = cent - winsize / 2., cent + winsize / 2.
-        wlo, whi = np.searchsorted(t, lo_edge), np.searchsorted(t, hi_edge)
-        blo, bhi = np.searchsorted(t, cent - stepsize / 2.), np.searchsorted(t, cent + stepsize / 2.)
-        if whi == n:
-            whi -= 1
-        gap_above = t[whi] < hi_edge - gapthreshold
-        gap_below = t[wlo] > lo_edge + gapthreshold
-        if gap_above and not gap_below:
-            wlo = np.searchsorted(t, t[whi] - winsize)
-        elif gap_below and not gap_above:
-            whi = np.searchsorted(t, t[wlo] + winsize)
-        rows[s] = (wlo, blo, bhi, whi)
-    return rows
+class Workspace(object):
+    """Device buffers and stream of the batched pre-fit steps (nmb_flat handle), grown on demand."""
+
+    def __init__(self):
+        h = ctypes.c_void_p()
+        check(load().nmb_flat_create(ctypes.byref(h)), "Workspace")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().nmb_flat_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def _owned(rows):
-    """Part of each box that survives the reference's sequential loop: where boxes overlap, the later
-    step overwrites the earlier one."""
-    nsteps = len(rows)
-    own = np.empty((nsteps, 2), dtype=np.int64)
-    nxt = np.iinfo(np.int64).max
-    # boxes are ordered (blo and bhi non-decreasing), so a point of box s is overwritten iff it lies
-    # at or beyond the smallest blo among the later, non-empty boxes (and inside that box, which the
-    # ordering guarantees up to that box's bhi; anything beyond is handled by even later boxes)
-    for s in range(nsteps - 1, -1, -1):
-        blo, bhi = rows[s, 1], rows[s, 2]
-        own[s] = (blo, max(blo, min(bhi, nxt)))
-        if bhi > blo:
-            nxt = min(nxt, blo)
-    return own
+_default_ws = None
+
+
+def _workspace(ws):
+    global _default_ws
+    if ws is not None:
+        return ws
+    if _default_ws is None or not _default_ws._h:
+        _default_ws = Workspace()
+    return _default_ws
+
+
+def _pad(columns, fill):
+    """List of 1-D arrays -> ([ncand, stride] array, lengths)."""
+    n = np.array([len(c) for c in columns], dtype=np.int64)
+    out = np.full((len(columns), int(n.max())), fill, dtype=np.float64)
+    for i, c in enumerate(columns):
+        out[i, :n[i]] = c
+    return out, n
+
+
+def ReduceNoiseBatch(lcs, winsize=2, stepsize=0.2, polydegree=3, niter=20, sigmaclip=3., gapthreshold=1.0, workspace=None):
+    """``ReduceNoise`` for a list of light curves ([N_c, 3] each, ragged lengths allowed) in ONE device call.
+    Returns the list of detrended copies (time, detrended flux, original flux_err); candidate c of the batch has
+    the bits ``ReduceNoise(lcs[c], ...)`` gives on its own."""
+    lcs = [np.asarray(lc, dtype=np.float64) for lc in lcs]
+    for lc in lcs:
+        if lc.ndim != 2 or lc.shape[1] < 3:
+            raise ValueError("every light curve must have shape [N, 3] (time, flux, flux_err)")
+    base = [np.median(lc[:, 1]) for lc in lcs]                      # lcbase (k2flatten.py:62)
+    t, n = _pad([lc[:, 0] - lc[0, 0] for lc in lcs], 0.0)           # JD0 shift (:59-60)
+    f, _ = _pad([lc[:, 1] / b for lc, b in zip(lcs, base)], 1.0)
+    e, _ = _pad([lc[:, 2] / b for lc, b in zip(lcs, base)], 1.0)
+    out = np.zeros_like(t)
+    ws = _workspace(workspace)
+    check(load().nmb_flatten_batch(ws._h, ptr(t), ptr(f), ptr(e), ptr(n), len(lcs), t.shape[1], float(winsize),
+                                   float(stepsize), float(gapthreshold), int(polydegree), int(niter), float(sigmaclip),
+                                   ptr(out)), "ReduceNoise")
+    return [np.column_stack((lc[:, 0], out[i, :n[i]], lc[:, 2])) for i, lc in enumerate(lcs)]
 
 
 def ReduceNoise(lc2, winsize=2, stepsize=0.2, polydegree=3, niter=20, sigmaclip=3., gapthreshold=1.0):
@@ -62,19 +83,31 @@ def ReduceNoise(lc2, winsize=2, stepsize=0.2, polydegree=3, niter=20, sigmaclip=
     degree-``polydegree`` polynomial fitted to its surrounding ``winsize`` window subtracted and 1 added.
     Same signature, defaults and output layout (time, detrended flux, original flux_err) as the
     reference; points that no box covers stay 0, as there."""
-    lc = np.array(lc2, dtype=np.float64, copy=True)
+    lc = np.asarray(lc2, dtype=np.float64)
     if lc.ndim != 2 or lc.shape[1] < 3:
         raise ValueError("lc must have shape [N, 3] (time, flux, flux_err)")
-    out = np.column_stack((lc[:, 0], np.zeros(len(lc)), lc[:, 2]))
-    t = lc[:, 0] - lc[0, 0]
-    lcbase = np.median(lc[:, 1])
-    f = lc[:, 1] / lcbase
-    e = lc[:, 2] / lcbase
-    rows = step_windows(t, winsize, stepsize, gapthreshold)
-    own = _owned(rows)
-    steps = np.ascontiguousarray(np.hstack([rows, own]), dtype=np.int32)
-    flux = np.zeros(len(lc))
-    check(load().nmb_flatten(ptr(as_f64(t)), ptr(as_f64(f)), ptr(as_f64(e)), len(t), ptr(steps), len(steps),
-                             float(winsize), int(polydegree), int(niter), float(sigmaclip), ptr(flux)), "ReduceNoise")
-    out[:, 1] = flux
-    return out
+    return ReduceNoiseBatch([lc], winsize, stepsize, polydegree, niter, sigmaclip, gapthreshold)[0]
+
+
+def AnomCutDiffBatch(fluxes, thresh=4.2, workspace=None):
+    """``AnomCutDiff`` (namaste.py:1459-1467) for a list of NaN-free flux series in one device call: list of boolean
+    masks of the points to KEEP."""
+    cols = [as_f64(f).reshape(-1) for f in fluxes]
+    flux, n = _pad(cols, 1.0)
+    keep = np.zeros(flux.shape, dtype=np.uint8)
+    ws = _workspace(workspace)
+    check(load().nmb_anomcut_batch(ws._h, ptr(flux), ptr(n), len(cols), flux.shape[1], float(thresh), ptr(keep)), "AnomCutDiff")
+    return [keep[i, :n[i]].astype(bool) for i in range(len(cols))]
+
+
+def window_mask_batch(times, tcen, width, two_sided=False, workspace=None):
+    """The fit window of ``RunMCMC`` (namaste.py:550-556) for a list of time arrays: ``abs(t - tcen < width)`` -- the
+    reference's quirk, which keeps everything before ``tcen + width`` -- or ``|t - tcen| < width``."""
+    cols = [as_f64(t).reshape(-1) for t in times]
+    t, n = _pad(cols, 0.0)
+    keep = np.zeros(t.shape, dtype=np.uint8)
+    ws = _workspace(workspace)
+    tc, wd = as_f64(np.broadcast_to(tcen, len(cols))), as_f64(np.broadcast_to(width, len(cols)))
+    check(load().nmb_window_mask_batch(ws._h, ptr(t), ptr(n), len(cols), t.shape[1], ptr(tc), ptr(wd),
+                                       1 if two_sided else 0, ptr(keep)), "window_mask")
+    return [keep[i, :n[i]].astype(bool) for i in range(len(cols))]

@@ -87,7 +87,8 @@ class EnsembleSampler(object):
         seed = ctypes.c_uint64(_seed_from(rstate0, self._seed0))
         if self._gp is not None:
             kind, kfull, mask = self._gpspec
-            check(lib.nmb_sampler_create_gp(self._lc._h, self.k, kind, ptr(as_f64(kfull)), mask, ptr(tab), seed, self.a,
+            kf = as_f64(kfull)  # keep the converted array alive across the call
+            check(lib.nmb_sampler_create_gp(self._lc._h, self.k, kind, ptr(kf), mask, ptr(tab), seed, self.a,
                                             ctypes.byref(h)), "EnsembleSampler")
         else:
             check(lib.nmb_sampler_create(self._lc._h, self.k, ptr(tab), seed, self.a, MODES[self._mode],
