@@ -44,8 +44,9 @@ constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-t
 #define NMB_EVAL_MINB 5          // resident stage-2 blocks per SM of the default arithmetic (96 registers)
 #endif
 #ifndef NMB_SWEEP_MINB
-#define NMB_SWEEP_MINB 7         // resident 128-walker sweep blocks per SM (72 registers: no spills with four timestamps per trip;
-                                 // measured on the 65 k x 4096 sweep: 0.664 ms against 0.692 at 8 blocks and 0.671 at 6)
+#define NMB_SWEEP_MINB 6         // resident 128-walker sweep blocks per SM (80 registers: no spills with eight timestamps per
+                                 // trip).  Measured on the 65 k x 4096 sweep (S = 15) / the 500 k x 2048 one (S = 10):
+                                 // 4 per trip at 8 blocks 0.692 ms, at 7 blocks 0.662 / 1.714, 8 per trip at 6 blocks 0.652 / 1.632
 #endif
 
 // Per-stage device timing (nmb_stage_timing / nmb_stage_times): CUDA events around stage 1 and

@@ -203,7 +203,7 @@ __device__ __forceinline__ int sweep_qmin(double vel, double ti, const double (&
     return qmin;
 }
 #ifndef NMB_SWEEP_TRIP
-#define NMB_SWEEP_TRIP 4
+#define NMB_SWEEP_TRIP 8
 #endif
 constexpr int kSweepTrip = NMB_SWEEP_TRIP;  // timestamps per trip of the sweep's inner loop (even, divides the chunk)
 
