@@ -808,9 +808,19 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, cons
             // lane order so the partials do not depend on how slots were merged
             const int nts = tend - t0;
             const int nsamp = nts * Sx;
-            for (int j = lane; j < nsamp; j += 32) {
-                const int h = j / Sx, k = j - h * Sx;
-                scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + t0 + h), __ldg(goff + k), wc, cf, &ws.wcs[cur_cw].q);
+            {   // the time and offset of the NEXT round are requested before this round's flux is evaluated
+                int h = lane / Sx, k = lane - h * Sx;
+                double ti = lane < nsamp ? __ldg(gt + t0 + h) : 0.0, ok_ = lane < nsamp ? __ldg(goff + k) : 0.0;
+                for (int j = lane; j < nsamp; j += 32) {
+                    const int slot = h * SP + k;
+                    const double ti_c = ti, ok_c = ok_;
+                    const int jn = j + 32;
+                    if (jn < nsamp) {
+                        h = jn / Sx; k = jn - h * Sx;
+                        ti = __ldg(gt + t0 + h); ok_ = __ldg(goff + k);
+                    }
+                    scratch[slot] = sample_flux_eval<PATH>(ti_c, ok_c, wc, cf, &ws.wcs[cur_cw].q);
+                }
             }
             __syncwarp();
             for (int h = lane; h < nts; h += 32) {
@@ -945,9 +955,19 @@ direct_eval_tail(DirectSmem<THREADS>& sm, const LcView& lc, const EvalWs& ws, co
         // flux and weight of the first 32 timestamps of the pass: requested before the flux rounds
         const double f_pre = lane < nts ? __ldg(gf + t0 + lane) : 0.0;
         const double w_pre = lane < nts ? __ldg(gw_ + t0 + lane) : 0.0;
-        for (int j = lane; j < nsamp; j += 32) {
-            const int h = j / Sx, k = j - h * Sx;
-            scratch[h * SP + k] = sample_flux_eval<PATH>(__ldg(gt + t0 + h), __ldg(goff + k), wc, cf, &wc.q);
+        {   // the time and offset of the NEXT round are requested before this round's flux is evaluated
+            int h = lane / Sx, k = lane - h * Sx;
+            double ti = lane < nsamp ? __ldg(gt + t0 + h) : 0.0, ok_ = lane < nsamp ? __ldg(goff + k) : 0.0;
+            for (int j = lane; j < nsamp; j += 32) {
+                const int slot = h * SP + k;
+                const double ti_c = ti, ok_c = ok_;
+                const int jn = j + 32;
+                if (jn < nsamp) {
+                    h = jn / Sx; k = jn - h * Sx;
+                    ti = __ldg(gt + t0 + h); ok_ = __ldg(goff + k);
+                }
+                scratch[slot] = sample_flux_eval<PATH>(ti_c, ok_c, wc, cf, &wc.q);
+            }
         }
         __syncwarp();
         if (lane == 0) trace_max(ws, 14);  // flux rounds of a direct pass done
