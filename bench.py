@@ -371,6 +371,14 @@ class Bench(object):
             raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
         torch.cuda.set_device(self.local)
         if self.world > 1:
+            # one disjoint set of host cores per rank: eight Python processes that wait on their GPUs otherwise
+            # migrate over each other (round 1: 72 -> 96 us per host call at 8 ranks)
+            try:
+                cores = sorted(os.sched_getaffinity(0))
+                share = max(1, len(cores) // self.world)
+                os.sched_setaffinity(0, set(cores[self.local * share:(self.local + 1) * share]) or set(cores))
+            except (AttributeError, OSError):
+                pass
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         import namaste_b200 as nb
         self.nb = nb
@@ -409,13 +417,19 @@ class Bench(object):
         return np.array([e0.elapsed_time(e1) for e0, e1 in evs]), t_begin, t_end
 
     def host_loop(self, fn, steps):
+        """`steps` host calls (each returns with its result on the host), wall-clock timed as a whole; the
+        per-call times are kept for the median."""
         self.barrier()
         self.torch.cuda.synchronize()
+        per = []
         t0 = time.perf_counter()
         res = None
         for _ in range(steps):
+            t1 = time.perf_counter()
             res = fn()
+            per.append(time.perf_counter() - t1)
         dt = time.perf_counter() - t0
+        self.last_host_median = float(np.median(per))
         return self.max_over_ranks(dt), res
 
 
@@ -487,7 +501,8 @@ def measure_lnprob(b, wl, staged, steps, warmup, with_clocks=False, variants=Tru
         b.host_loop(lambda: staged.lnprob(pos_h, pri_h, mode=mode), warmup)
         dt, got = b.host_loop(lambda: staged.lnprob(pos_h, pri_h, mode=mode), steps)
         assert np.allclose(np.asarray(got).reshape(ref_out.shape), ref_out, rtol=1e-12, atol=0, equal_nan=True), mode
-        res["e2e_" + mode] = {"value": units / (dt / steps), "unit": "wt/s", "ms_per_step": 1e3 * dt / steps}
+        res["e2e_" + mode] = {"value": units / (dt / steps), "unit": "wt/s", "ms_per_step": 1e3 * dt / steps,
+                              "ms_per_step_median": 1e3 * b.last_host_median}
     res["h2d"] = int(pos_h.size * 8 + ptab.size * 8)
     res["d2h"] = int(C * W * 8)
     res["ref_out"] = ref_out
@@ -763,7 +778,7 @@ def run_ours(args):
         "clocks": head.get("clocks"),
         "e2e": {"value": head["e2e_brute"]["value"], "unit": "wt/s",
                 "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
-                "ms_per_step": head["e2e_brute"]["ms_per_step"],
+                "ms_per_step": head["e2e_brute"]["ms_per_step"], "ms_per_step_median": head["e2e_brute"]["ms_per_step_median"],
                 "note": "LightCurve.lnprob(numpy params, priors) -> numpy lnprob, brute force like `value`; light curve "
                         "staged once like emcee args="},
         "e2e_callable": e2e_callable,
