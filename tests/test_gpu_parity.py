@@ -221,3 +221,26 @@ def test_results_do_not_depend_on_the_launch_shape(nb):
             part = lc.lnprob(pos[lo:hi], g["priors"], mode=mode)
             assert np.array_equal(part, full[lo:hi], equal_nan=True), (mode, lo, hi)
     lc.close()
+
+
+def test_literal_callable_finds_its_staged_light_curve(nb):
+    """MonoOnlyLogProb(params, lc ndarray, priors, model) -- the reference's call (namaste.py:590, emcee args=) --
+    stages `lc` once and finds it again by address + content; an in-place edit is seen, and a read-only array is
+    keyed by identity alone."""
+    from namaste_b200 import namaste as host
+    g = load_golden("kat_epic203311200")
+    pri = priors_from_table(g["priors"])
+    lc = g["lc"].copy()
+    host.clear_cache()
+    a = nb.MonoOnlyLogProb(g["params"], lc, pri)
+    assert len(host._LC_CACHE) == 1
+    b = nb.MonoOnlyLogProb(g["params"], lc, pri)
+    assert len(host._LC_CACHE) == 1 and np.array_equal(a, b)
+    lc[100, 1] *= 1.0 + 1e-6                                   # same address, one flux value changed
+    c = nb.MonoOnlyLogProb(g["params"], lc, pri)
+    assert len(host._LC_CACHE) == 2 and not np.array_equal(a, c)
+    frozen = g["lc"].copy()
+    frozen.setflags(write=False)
+    d = nb.MonoOnlyLogProb(g["params"], frozen, pri)
+    assert np.array_equal(d, a) and len(host._fingerprint(frozen)) == 4
+    host.clear_cache()

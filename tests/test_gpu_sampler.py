@@ -130,3 +130,45 @@ def test_runmcmc_driver(nb):
     assert abs(med[0] - best[0]) < 0.01            # tcen [d]
     assert abs(med[3] - best[3]) < 0.01            # RpRs
     assert np.median(smp[:, 6]) >= np.median(s.lnprobability[:, 0])   # the ensemble moved uphill from the PDF draws
+
+
+def test_split_sampler_on_one_rank_is_the_plain_sampler(nb):
+    """The walker-split driver (nmb_sampler_run_split) with a world of one -- what a single-GPU box can exercise --
+    gives the chain of EnsembleSampler bit for bit, stored or not; the multi-rank form is checked by
+    tests/multigpu_check.py on 2, 4 and 8 GPUs."""
+    from namaste_b200.distributed import SplitEnsembleSampler
+    lc, pri, pos0 = _problem()
+    staged = nb.LightCurve(lc)
+    plain = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(staged, pri), seed=99)
+    plain.run_mcmc(pos0, 12)
+    split = SplitEnsembleSampler(staged, pri, 24, seed=99)
+    assert split.transport == "local"
+    split.run_mcmc(pos0, 5)
+    pos, lnp = split.run_mcmc(None, 7)
+    assert np.array_equal(split.chain, plain.chain) and np.array_equal(split.lnprobability, plain.lnprobability)
+    assert np.array_equal(split.naccepted, plain.naccepted)
+    assert np.array_equal(pos, plain.chain[:, -1, :]) and np.array_equal(lnp, plain.lnprobability[:, -1])
+    quiet = SplitEnsembleSampler(staged, pri, 24, seed=99)
+    p2, l2 = quiet.run_mcmc(pos0, 12, storechain=False)
+    assert np.array_equal(p2, pos) and quiet.chain.shape == (24, 0, 6)
+
+
+def test_split_api_refuses_bad_arguments(nb):
+    import ctypes
+    from namaste_b200._lib import load, ptr
+    from namaste_b200.distributed import SplitEnsembleSampler
+    lc, pri, pos0 = _problem()
+    staged = nb.LightCurve(lc)
+    s = SplitEnsembleSampler(staged, pri, 24, seed=1)
+    lib = load()
+    handles = np.zeros(64 * 4, dtype=np.uint8)
+    assert lib.nmb_sampler_split_export(s._h, ptr(handles)) == 0 and handles[:64].any()
+    assert lib.nmb_sampler_split_attach(s._h, 0, 17, ptr(handles)) < 0          # more ranks than the library maps
+    assert lib.nmb_sampler_split_attach(s._h, 3, 2, ptr(handles)) < 0           # rank outside the world
+    assert lib.nmb_sampler_split_attach(s._h, 0, 5, ptr(handles)) < 0           # 12 walkers per half do not divide by 5
+    assert lib.nmb_sampler_run_split(s._h, 1, 0) < 0                            # no state yet
+    assert b"never been called" in lib.nmb_last_error()
+    with pytest.raises(ValueError):
+        SplitEnsembleSampler(staged, pri, 24, seed=1, transport="carrier pigeon")
+    with pytest.raises(ValueError):
+        SplitEnsembleSampler(nb.LightCurve([lc, lc]), pri, 24, seed=1)              # one light curve only
