@@ -701,9 +701,16 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, cons
     // chunks of slots: the first chunk of a warp is its own index (no atomic on the way to the first
     // sample), further chunks come from a shared counter, fetched one chunk ahead.  Small queues are
     // dealt out in one chunk per warp; large ones in chunks of at least one merged pass.
-    const int merge = ws.merge;
     const int per = (total + nwarps - 1) / nwarps;
-    const int chunk = per <= merge ? max(1, per) : max(merge, total / (nwarps * 8));
+    // slots a warp evaluates in one pass: the staged default, one more when the queue is short (a few slots per
+    // warp: the warps' latency chains -- slot record, walker constants, completion count -- weigh more than the
+    // balance of the last chunks).  A queue of up to two passes per warp is dealt out statically, one chunk per
+    // warp and no work-fetching atomic; measured on the 2048-walker half-steps of the 65 k-point light curve,
+    // S = 15: 67 -> 61 us with three slots per pass, -> 52 us with the static deal up to two passes
+    // (profiles/r02v_ab_stage2_short_queue.txt); its 4096-walker evaluation with prior-box walkers, 40 slots per
+    // warp, prefers two slots per pass and fetched chunks.  Results do not depend on either (see SlotRec).
+    const int merge = per <= 8 ? min(kEvalMerge, ws.merge + 1) : ws.merge;
+    const int chunk = per <= 2 * merge ? max(1, per) : max(merge, total / (nwarps * 8));
     const int nchunks = (total + chunk - 1) / chunk;
     int* queue = ws.counters + 2;
     int ch_cur = gw, ch_nxt = INT_MAX;
