@@ -162,14 +162,18 @@ __device__ __forceinline__ void push_slots(const EvalWs& ws, long long cw, int l
 // A block owns WPB*32 walkers (one per thread, constants in registers) and a span of `gpb`
 // reduction granules of one light curve.  The span streams through shared memory in chunks of CH
 // timestamps: two TMA bulk copies per chunk (t and the precomputed chi^2 terms w*(f-1)^2) into a
-// double buffer.  The inner loop costs, per walker and fine sample, two DFMA
-//   vx' = fma(vel, t_i, ck),  ck = fma(vel, off_k, -vel*tcen)  (S registers per walker),
-//   q'  = fma(vx', vx', b^2)
-// and a third of an integer 3-input min on the high words (VIMNMX3); t_i is one broadcast LDS per
-// timestamp.  A DFMA holds the issue port for two cycles on this part and every other instruction
+// double buffer.  The inner loop costs, per walker and fine sample, ONE DFMA
+//   y = fma(V, t_i, c_k),  V = vel s,  c_k = fma(vel, off_k, -vel*tcen) s,  s = 2 / X  (S registers per walker)
+// -- the walker's position along the chord in units of half the half-width X of its in-transit window (SweepConsts,
+// lnprob_kernels.cuh) -- and half of a 3-input LOP3: a sample can be inside the limb only if |y| < 2, i.e. bit 30 of
+// hi32(y) is clear, so "some sample may be in transit" is the AND of the high words.
+// (Round 1 and most of round 2 squared the position, q' = fma(vx', vx', b^2), and took the integer minimum of the
+// high words against (1 + p)^2: two DFMA and half a VIMNMX3 -- a two-cycle instruction on this part -- per sample.
+// The interval test classifies the same samples with half the FP64 work and full-rate logic.)  t_i is one
+// broadcast LDS per timestamp.  A DFMA holds the issue port for two cycles on this part and every other instruction
 // for one, so the loop is written to keep non-FP64 instructions per sample to a minimum.  (The
-// run-time-S instantiation reads a table ft[i][k] = t_i + off_k built per chunk instead.)  A timestamp whose S samples all have
-// hi32(q') > hi32(q_thr) is provably outside the limb (see make_walker_consts) and adds its
+// run-time-S instantiation reads a table ft[i][k] = t_i + off_k built per chunk instead.)  A timestamp whose S samples
+// all fall outside the window is provably outside the limb (see make_sweep_consts) and adds its
 // precomputed term; the others only widen the walker's in-transit range, kept in registers and
 // merged with one atomicMin/Max per thread.  Per-(granule, walker) partial sums go to HBM
 // (coalesced) and are folded in granule order by the last block of each walker group, which makes
@@ -187,20 +191,17 @@ struct WalkSmem {
     int flag;
 };
 
-// min over the S supersamples of one timestamp of hi32(q'), q' = fma(vx', vx', b^2), vx' = fma(vel, t_i, ck[k]):
-// 2 S DFMA and ceil(S / 2) three-input integer minima
+// AND over the S supersamples of one timestamp of hi32(y), y = fma(V, t_i, ck[k]): S DFMA and ceil(S / 2)
+// three-input logic operations.  Bit 30 of the result is clear iff some sample has |y| < 2.
 template <int S>
-__device__ __forceinline__ int sweep_qmin(double vel, double ti, const double (&ck)[S > 0 ? S : 1], double b2) {
-    int h[S > 0 ? S : 1];
+__device__ __forceinline__ unsigned sweep_yand(double vs, double ti, const double (&ck)[S > 0 ? S : 1]) {
+    unsigned h[S > 0 ? S : 1];
 #pragma unroll
-    for (int k = 0; k < S; ++k) {
-        const double vx = fma(vel, ti, ck[k]);
-        h[k] = __double2hiint(fma(vx, vx, b2));
-    }
-    int qmin = (S & 1) ? h[S - 1] : min(h[S - 2], h[S - 1]);
+    for (int k = 0; k < S; ++k) h[k] = (unsigned)__double2hiint(fma(vs, ti, ck[k]));
+    unsigned a = (S & 1) ? h[S - 1] : (h[S - 2] & h[S - 1]);
 #pragma unroll
-    for (int k = 0; k + 1 < S - ((S & 1) ? 0 : 2); k += 2) qmin = min(qmin, min(h[k], h[k + 1]));
-    return qmin;
+    for (int k = 0; k + 1 < S - ((S & 1) ? 0 : 2); k += 2) a &= h[k] & h[k + 1];
+    return a;
 }
 #ifndef NMB_SWEEP_TRIP
 #define NMB_SWEEP_TRIP 8
@@ -246,8 +247,8 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
 
     // per-walker constants (every block of the walker group derives them; the first one publishes
     // what stage 2 and the finalisation need: proposal and model constants)
-    double vel = 0.0, nvtc = 0.0, b2 = 0.0;
-    int qhi = -1;  // padding lanes never hit
+    SweepConsts swc = {0.0, 4.0, 1.0, 0.0};  // padding lanes never hit
+    const double span = lc.off[(long long)cand * Sx + Sx - 1];  // staged light curve: read before the grid dependency
     if (active) {
         double par[6];
         if (sc.enabled) {
@@ -260,19 +261,20 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
             for (int d = 0; d < 6; ++d) par[d] = params[cw * 6 + d];
         }
         const WalkerConsts wc = make_walker_consts(par, Sx);
-        vel = wc.vel; nvtc = wc.nvtc; b2 = wc.b2; qhi = wc.qhi;
+        swc = make_sweep_consts(wc, span);
         if (tb == 0) ws.wcs[cw] = wc;
     }
     __syncthreads();  // mbarrier init and offsets visible
     if (tid == 0) trace_max(ws, 1);  // constants ready
-    // compiled-in S: the walker's S sample offsets live in registers, ck = vel * off_k - vel * tcen, so a
-    // fine sample is vx' = fma(vel, t_i, ck) with t_i one broadcast load per timestamp and no table
+    // compiled-in S: the walker's S sample offsets live in registers, ck = (vel * off_k - vel * tcen) * s, so a
+    // fine sample is y = fma(V, t_i, ck) with t_i one broadcast load per timestamp and no table
     double ck[S > 0 ? S : 1];
     if (S > 0) {
 #pragma unroll
-        for (int k = 0; k < S; ++k) ck[k] = fma(vel, sm.off[k], nvtc);
+        for (int k = 0; k < S; ++k) ck[k] = fma(swc.vel, sm.off[k], swc.nvtc) * swc.s;
     }
 
+    const double vs = swc.vs, c0s = swc.nvtc * swc.s;
     double acc = 0.0;
     int lo = INT_MAX, hi = 0;
     double* __restrict__ prow = ws.partials + (long long)cand * ngran * W + w;
@@ -287,7 +289,10 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
                 ft[i * SP + k] = tr[i] + sm.off[k];
             }
         }
-        __syncthreads();  // every thread is past the previous chunk (and the table is complete)
+        // every thread is past the previous chunk (and the table is complete).  (A ring of four buffers with
+        // per-buffer "empty" barriers instead of this block-wide one -- warps free to drift two chunks apart -- was
+        // measured and is slower: 0.474 against 0.448 ms on the 65 k x 4096 sweep, profiles/r02a2_ab_sweep_ring.txt.)
+        __syncthreads();
         if (tid == 0 && c + 1 < c_end) {
             mbar_expect_tx(&sm.mbar[buf ^ 1], 2u * CH * sizeof(double));
             tma_bulk_g2s(sm.traw[buf ^ 1], gt + (long long)(c + 1) * CH, CH * sizeof(double), &sm.mbar[buf ^ 1]);
@@ -304,14 +309,14 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
         }
         if (S > 0) {
             // NT timestamps per trip.  The common case -- none of them can be in transit -- costs, beside the
-            // 2 S DFMA and S / 2 integer minima per timestamp, one more minimum, a compare and a branch per
+            // S DFMA and S / 2 logic operations per timestamp, one more AND, a bit test and a branch per
             // trip and one DADD per timestamp; the per-timestamp book-keeping runs only on the rare trips that
             // touch the transit.  Terms are added in timestamp order on both paths.
             constexpr int NT = kSweepTrip;
 #pragma unroll 1
             for (int i0 = 0; i0 < CH; i0 += NT) {
                 double tt[NT], mm[NT];
-                int q[NT];
+                unsigned q[NT];
 #pragma unroll
                 for (int j = 0; j < NT; j += 2) {
                     const double2 tv = *reinterpret_cast<const double2*>(tr + i0 + j);
@@ -319,19 +324,19 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
                     tt[j] = tv.x; tt[j + 1] = tv.y;
                     mm[j] = mv.x; mm[j + 1] = mv.y;
                 }
-                int qall = INT_MAX;
+                unsigned qall = 0xffffffffu;
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    q[j] = sweep_qmin<S>(vel, tt[j], ck, b2);
-                    qall = min(qall, q[j]);
+                    q[j] = sweep_yand<S>(vs, tt[j], ck);
+                    qall &= q[j];
                 }
-                if (qall > qhi) {
+                if (qall & kSweepOutBit) {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) acc += mm[j];
                 } else {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        if (q[j] > qhi) {
+                        if (q[j] & kSweepOutBit) {
                             acc += mm[j];
                         } else {
                             lo = min(lo, base + i0 + j);
@@ -343,13 +348,10 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
         } else {
 #pragma unroll 2
             for (int i = 0; i < CH; ++i) {
-                int qmin = INT_MAX;
+                unsigned yand = 0xffffffffu;
                 const double* row = sm.ftab[buf] + i * SP;
-                for (int k = 0; k < Sx; ++k) {
-                    const double vx = fma(vel, row[k], nvtc);
-                    qmin = min(qmin, __double2hiint(fma(vx, vx, b2)));
-                }
-                const bool hit = qmin <= qhi;
+                for (int k = 0; k < Sx; ++k) yand &= (unsigned)__double2hiint(fma(vs, row[k], c0s));
+                const bool hit = !(yand & kSweepOutBit);
                 const double term = tm[i];
                 if (!hit) acc += term;
                 if (hit) {

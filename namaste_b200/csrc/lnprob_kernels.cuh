@@ -48,13 +48,52 @@ struct WalkerConsts {
     double tcen, vel, b2;
     double qthr;   // conservative bound: fma(vx,vx,b2) > qthr  =>  sqrt(b2 + vx*vx) > 1 + p   (vx faithful)
     double fbar;   // mean of S out-of-transit samples (== 1.0 unless the LD coefficients are inf/NaN)
-    double nvtc;   // -(vel * tcen): vx' = fma(vel, ft, nvtc) is the 1-FMA position used by the sweep
-    double qthr_c; // conservative bound for q' = fma(vx', vx', b2), covers the cancellation error of vx'
-    int qhi;       // high word of qthr_c (INT_MAX if any sweep constant is not finite): a sample is a
-                   // candidate iff hi32(q') <= qhi, an integer compare that keeps the FP64 pipe for FMAs
-    int pad_;
     QuadConsts q;
 };
+
+// Classification constants of the brute-force sweep (sweep_walkers_kernel): ONE fma per fine sample,
+//   y = fma(V, t_i, c_k),  V = vel s,  c_k = fma(vel, off_k, -vel*tcen) s,  s = 2 / X,
+// i.e. y = 2 vx / X with vx the walker's position along the chord and X the half-width of its in-transit window:
+// the sample can only be inside the limb if |y| < 2, which for an IEEE double is ONE BIT -- bit 30 of the high
+// word (the top bit of the biased exponent) is clear -- whatever the sign.  "Some sample of these timestamps may
+// be in transit" is then the AND of the high words, a full-rate 3-input LOP3 per two samples.
+// X bounds |vx| of every sample the reference puts inside the limb:
+//   the reference forms vx_r = fl(vel * fl(fl(t_i + off_k) - tcen)) and z = sqrt(fl(b2 + fl(vx_r^2))); with
+//   Xq = sqrt(qthr - b2), |vx_r| > Xq implies z > 1 + p (see qthr).  Against the exact product
+//   vx_e = vel (t_i + off_k - tcen):  |vx_r - vx_e| <= u (|vel tcen| + 3 |vx_r|)  (u = 2^-53 = kEps / 2), and the
+//   computed y / s - vx_e collects the roundings of vel*tcen, of c_k (twice), of V (times t_i, and
+//   |vel t_i| <= |vel tcen| + |vel| span + X inside the window) and of the last fma:
+//   in total <= u (5 |vel tcen| + 3 |vel| span + 5 X)  (span = off_{S-1}).
+//   X = (Xq + kEps (4 |vel tcen| + 2 |vel| span)) (1 + 64 kEps) exceeds Xq by more than that, and s is rounded
+//   down so that {|y| < 2} contains {|vx| <= X}: the window is a superset of the reference's in-transit samples.
+// Samples inside the window are not assumed to be in transit -- stage 2 classifies them faithfully.
+struct SweepConsts {
+    double vel, nvtc, s, vs;   // c_k = fma(vel, off_k, nvtc) * s,  V = vs
+};
+constexpr unsigned kSweepOutBit = 0x40000000u;   // set in hi32(y)  <=>  |y| >= 2 (or y not finite)
+__device__ __forceinline__ SweepConsts make_sweep_consts(const WalkerConsts& w, double span) {
+    const SweepConsts always = {0.0, 0.0, 1.0, 0.0};   // y == 0: every sample goes to stage 2
+    const SweepConsts never = {0.0, 4.0, 1.0, 0.0};    // y == 4: no sample can be in transit
+    const double vtc = w.vel * w.tcen;
+    const double hx2 = w.qthr - w.b2;   // one rounding of the exact difference of the two doubles
+    const bool finite = (fabs(w.vel) <= 1e100) && (fabs(vtc) <= 1e100) && (w.b2 <= 1e100) && (fabs(w.qthr) <= 1e100) &&
+                        (fabs(span) <= 1e100);
+    // the sweep adds the precomputed term w*(f-1)^2 for out-of-transit timestamps, which assumes an
+    // out-of-transit model of exactly 1; if the limb-darkening normalisation is degenerate
+    // (fout != 1, e.g. 1 - LD1/3 - LD2/6 == 0 or non-finite coefficients) every sample goes to stage 2
+    if (!finite || !(w.fbar == 1.0)) return always;
+    if (!(hx2 >= 0.0)) return never;   // p == 0 (qthr = -1) or |b| beyond the limb: never in transit
+    const double xq = ::sqrt(hx2) * (1.0 + 4 * kEps);
+    const double ev = kEps * (4 * fabs(vtc) + 2 * fabs(w.vel) * fabs(span));
+    const double X = (xq + ev) * (1.0 + 64 * kEps);
+    if (!(X >= 1e-100)) return always;   // degenerate window (vel == 0 at the limb): the scale 2 / X is not usable
+    SweepConsts c;
+    c.s = (2.0 / X) * (1.0 - 4 * kEps);
+    c.vel = w.vel;
+    c.nvtc = -vtc;
+    c.vs = w.vel * c.s;
+    return c;
+}
 
 // mean of S copies of x in NumPy's pairwise order (bin_mean of a constant bin)
 __device__ __forceinline__ double bin_mean_const(double x, int S) {
@@ -81,23 +120,6 @@ __device__ __forceinline__ WalkerConsts make_walker_consts(const double* par, in
     // rounding slack: q_fma and q_faithful differ by < 2 ulp, sqrt rounds by 1/2 ulp
     w.qthr = (w.q.p == 0.0) ? -1.0 : (w.q.onep * w.q.onep) * (1.0 + 16 * kEps);
     w.fbar = (w.q.fout == 1.0) ? 1.0 : bin_mean_const(w.q.fout, S);
-    // sweep position vx' = fma(vel, t_i, ck), ck = fma(vel, off_k, -vel*tcen): against the reference's
-    // vx = fl(vel * fl(fl(t_i + off_k) - tcen)) it carries the rounding of ck, of the final fma and of
-    // the reference's own ft and x:  |vx' - vx| <= 2 eps (|vel tcen| + |vel| off_k) + 3 eps |vx'|
-    // (off_k < one cadence < 1 day), hence
-    // q' > (e + sqrt(e^2 + (1+p)^2))^2 (1 + O(eps))  =>  the faithful z exceeds 1+p
-    const double vtc = w.vel * w.tcen;
-    w.nvtc = -vtc;
-    const double ev = kEps * (2 * fabs(vtc) + 2 * fabs(w.vel));
-    const double u = (ev + ::sqrt(ev * ev + w.q.onep * w.q.onep)) * (1.0 + 32 * kEps);
-    w.qthr_c = (w.q.p == 0.0) ? -1.0 : u * u * (1.0 + 8 * kEps);
-    // q' >= 0 for finite inputs, so its IEEE bit pattern orders like an integer
-    const bool finite = (fabs(w.vel) <= 1e300) && (fabs(vtc) <= 1e300) && (w.b2 <= 1e300) && (w.qthr_c <= 1e300);
-    // the sweep adds the precomputed term w*(f-1)^2 for out-of-transit timestamps, which assumes an
-    // out-of-transit model of exactly 1; if the limb-darkening normalisation is degenerate
-    // (fout != 1, e.g. 1 - LD1/3 - LD2/6 == 0 or non-finite coefficients) every sample goes to stage 2
-    w.qhi = (!finite || !(w.fbar == 1.0)) ? INT_MAX : (w.qthr_c < 0.0 ? -1 : __double2hiint(w.qthr_c));
-    w.pad_ = 0;
     return w;
 }
 
