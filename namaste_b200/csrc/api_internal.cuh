@@ -211,13 +211,13 @@ inline int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
         CU(cudaMalloc(&ws.slots, cap * sizeof(nmb::SlotRec)));
         CU(cudaMalloc(&ws.slotpart, cap * sizeof(double)));
         CU(cudaMalloc(&ws.grouptick, CW * sizeof(int)));
-        CU(cudaMalloc(&ws.counters, 4 * sizeof(int)));
+        CU(cudaMalloc(&ws.counters, 8 * sizeof(int)));
         if (std::getenv("NMB_TRACE")) {
             CU(cudaMalloc(&ws.trace, 16 * sizeof(unsigned long long)));
             CU(cudaMemsetAsync(ws.trace, 0, 16 * sizeof(unsigned long long), st));
         }
         CU(cudaMemsetAsync(ws.grouptick, 0, CW * sizeof(int), st));
-        CU(cudaMemsetAsync(ws.counters, 0, 4 * sizeof(int), st));
+        CU(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(int), st));
         nmb::init_ranges_kernel<<<(unsigned)((CW + 255) / 256), 256, 0, st>>>(ws.rlo, ws.rhi, ws.slotsdone, (int)CW);
         g_launches++;
         CU(cudaGetLastError());
@@ -391,11 +391,11 @@ template <int S, int PATH, int THREADS>
 int launch_direct_t(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                     cudaStream_t st, const nmb::SampleCtx& sc, int* resident_out) {
     auto kern = nmb::window_direct_kernel<S, THREADS, 512 / THREADS, PATH>;
-    const size_t smem = sizeof(nmb::DirectSmem<THREADS>);
-    static thread_local int resident = 0;
+    const size_t smem = std::max(sizeof(nmb::DirectSmem<THREADS>), sizeof(nmb::EvalSmem<THREADS>));
+    static thread_local int resident = 0, sms = 0;
     if (!resident) {
         if (int rc = set_smem(kern, smem)) return rc;
-        int dev = 0, sms = 0, per_sm = 0;
+        int dev = 0, per_sm = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
@@ -403,8 +403,11 @@ int launch_direct_t(nmb_lc* lc, const double* params, int W, const double* prior
     }
     if (resident_out) { *resident_out = resident; if (!params && !sc.enabled) return NMB_OK; }
     const size_t CW = (size_t)lc->ncand * W;
-    CU(launch_pdl(kern, dim3((unsigned)CW), dim3(THREADS), smem, st, lc->view(), params, W, priors, lc->ws, lnprob,
-                  loglike, sc));
+    // one queue worker per SM behind the direct blocks, in the same grid (see window_direct_kernel)
+    static const int work_bps = std::getenv("NMB_DIRECT_EVAL_BPS") ? std::max(1, std::atoi(std::getenv("NMB_DIRECT_EVAL_BPS"))) : 1;
+    const unsigned nwork = (unsigned)(sms * work_bps);
+    CU(launch_pdl(kern, dim3((unsigned)CW + nwork), dim3(THREADS), smem, st, lc->view(), params, W, priors, lc->ws, sms,
+                  lnprob, loglike, sc));
     g_launches++;
     return NMB_OK;
 }
@@ -454,14 +457,12 @@ int launch_window(nmb_lc* lc, const double* params, int W, const double* priors,
         g_launches++;
     }
     lc->timer.mark(1, st);
-    // one block per SM behind window_direct_kernel (measured: MCMC +1.3 % on config 2, +3.8 % on config 1)
-    static const int direct_bps = std::getenv("NMB_DIRECT_EVAL_BPS") ? std::atoi(std::getenv("NMB_DIRECT_EVAL_BPS")) : 1;
-    g_eval_blocks_per_sm = direct ? direct_bps : 0;
-    const int rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
-                         : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
-    g_eval_blocks_per_sm = 0;
+    // (window_direct_kernel carries its own queue workers: nothing to launch behind it)
+    const int rc = direct  ? NMB_OK
+                   : mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)
+                           : launch_eval<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype);
     lc->last_stage1 = direct ? "window_direct_kernel" : "window_ranges_kernel";
-    lc->last_stage2 = mixed ? "eval_mixed_kernel" : "eval_slots_kernel";
+    lc->last_stage2 = direct ? "window_direct_kernel(queue workers)" : mixed ? "eval_mixed_kernel" : "eval_slots_kernel";
     lc->timer.mark(2, st);
     lc->timer.done();
     return rc;

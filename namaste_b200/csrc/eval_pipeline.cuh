@@ -58,7 +58,8 @@ struct EvalWs {
     double* slotpart;    // [slotcap]  chi^2 partial of each slot
     int* slotsdone;      // [CW]  (0 when idle)
     int* grouptick;      // [C*walker blocks] finished time blocks per walker group (0 when idle)
-    int* counters;       // [1] slots pushed by stage 1 (queue tail), [2] next dynamically assigned chunk,
+    int* counters;       // [4] direct blocks of window_direct_kernel that have decided (evaluate / finish / queue);
+                         // [1] slots pushed by stage 1 (queue tail), [2] next dynamically assigned chunk,
                          // [3] stage-2 blocks finished; the last stage-2 block zeroes them
     int maxslots;        // slots per walker are capped; longer ranges put several passes in a slot
     int tsw;             // timestamps per slot: as many whole bins as fit in kEvalPass supersamples
@@ -679,7 +680,7 @@ struct EvalSmem {
 
 template <int S, int THREADS, int PATH, bool PACKED>
 __device__ __forceinline__ void
-eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, const double* __restrict__ params, int W,
+eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const int bid, const LcView& lc, const double* __restrict__ params, int W,
                 const double* __restrict__ priors, const EvalWs& ws, int nsm, double* __restrict__ lnprob,
                 double* __restrict__ loglike, const SampleCtx& sc) {
     constexpr int NWARP = THREADS / 32;
@@ -698,8 +699,7 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, cons
     const int nwarps = nblocks * NWARP;
     // (PACKED, eval_mixed_kernel: block after block instead, so that a short queue keeps few blocks busy and
     // the others leave their SM slots to the direct blocks at once)
-    const int gw = PACKED ? (int)blockIdx.x * NWARP + warp
-                          : (((int)blockIdx.x / nsm) * NWARP + warp) * nsm + (int)blockIdx.x % nsm;
+    const int gw = PACKED ? bid * NWARP + warp : ((bid / nsm) * NWARP + warp) * nsm + bid % nsm;
     // chunks of slots: the first chunk of a warp is its own index (no atomic on the way to the first
     // sample), further chunks come from a shared counter, fetched one chunk ahead.  Small queues are
     // dealt out in one chunk per warp; large ones in chunks of at least one merged pass.
@@ -899,6 +899,7 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const LcView& lc, cons
             ws.counters[1] = 0;
             ws.counters[2] = 0;
             ws.counters[3] = 0;
+            ws.counters[4] = 0;
         }
     }
 }
@@ -908,7 +909,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 eval_slots_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
                   int nsm, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    eval_slots_body<S, THREADS, PATH, false>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), (int)gridDim.x, lc, params, W,
+    eval_slots_body<S, THREADS, PATH, false>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), (int)gridDim.x, (int)blockIdx.x, lc, params, W,
                                              priors, ws, nsm, lnprob, loglike, sc);
 }
 
@@ -1024,7 +1025,7 @@ eval_mixed_kernel(LcView lc, const double* __restrict__ params, int W, const dou
     constexpr int NWARP = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x < nq) {
-        eval_slots_body<S, THREADS, PATH, true>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), nq, lc, params, W, priors, ws,
+        eval_slots_body<S, THREADS, PATH, true>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), nq, (int)blockIdx.x, lc, params, W, priors, ws,
                                                 nsm, lnprob, loglike, sc);
         return;
     }
@@ -1075,9 +1076,27 @@ eval_mixed_kernel(LcView lc, const double* __restrict__ params, int W, const dou
 template <int S, int THREADS, int MINB, int PATH>
 __global__ void __launch_bounds__(THREADS, MINB)
 window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const double* __restrict__ priors, EvalWs ws,
-                     double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
+                     int nsm, double* __restrict__ lnprob, double* __restrict__ loglike, SampleCtx sc) {
     constexpr int NWARP = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ndirect = W * lc.ncand;
+    if ((int)blockIdx.x >= ndirect) {
+        // ---- queue worker (the last blocks of the grid, dispatched after the direct blocks): waits until every
+        // direct block has decided what to do with its walker -- a block decides a few microseconds after it starts,
+        // long before its flux rounds --, then drains the queue like eval_slots_kernel.  Once an ensemble has left
+        // its initial prior-box walkers behind the queue is empty and the workers exit at once; the separate
+        // eval_slots launch that used to find it empty cost ~3 us of every half-step.  Direct blocks never wait
+        // for workers, and a worker only holds one of the SM's block slots, so the wait cannot deadlock.
+        pdl_wait();
+        if (threadIdx.x == 0) {
+            int spins = 0;
+            while (ld_acquire_gpu(ws.counters + 4) < ndirect && ++spins < (1 << 22)) __nanosleep(64);
+        }
+        __syncthreads();
+        eval_slots_body<S, THREADS, PATH, false>(*reinterpret_cast<EvalSmem<THREADS>*>(smem_raw), (int)gridDim.x - ndirect,
+                                                 (int)blockIdx.x - ndirect, lc, params, W, priors, ws, nsm, lnprob, loglike, sc);
+        return;
+    }
     DirectSmem<THREADS>& sm = *reinterpret_cast<DirectSmem<THREADS>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cw = blockIdx.x;
@@ -1093,7 +1112,7 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
     }
     const CandGeom geo = load_cand_geom(lc, cand, Sx);
     pdl_wait();     // walker positions come from the previous kernel
-    pdl_trigger();  // eval_slots_kernel may be scheduled; it waits for this grid to finish before reading
+    pdl_trigger();  // the next kernel may be scheduled; it waits for this grid to finish before reading
     if (tid == 0) trace_min(ws, 0);
 
     double p6[6];
@@ -1128,6 +1147,9 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
         return lp;
     };
 
+    const bool queued = nsl > 0 && (pps > 1 || nsl > ws.direct_cap);
+    // decided (nothing to publish unless the walker goes onto the queue): tell the queue workers
+    if (!queued && tid == 0) atomicAdd(ws.counters + 4, 1);
     if (nsl == 0) {  // never in transit
         if (warp == 0) {
             const double lp = ln_prior_w0();
@@ -1136,7 +1158,7 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
         if (tid == 0) trace_max(ws, 3);
         return;
     }
-    if (pps > 1 || nsl > ws.direct_cap) {  // too long for one block: onto the queue
+    if (queued) {  // too long for one block: onto the queue
         if (tid == 0) {
             sm.first = atomicAdd(ws.counters + 1, nsl);
             ws.oot[cw] = oot_words.value();
@@ -1152,7 +1174,12 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
             r.cw = cw; r.t0 = ilo + i * step; r.t1 = min(ihi, ilo + (i + 1) * step); r.first = first;
             *reinterpret_cast<int4*>(ws.slots + first + i) = *reinterpret_cast<const int4*>(&r);
         }
-        if (tid == 0) trace_max(ws, 3);
+        __syncthreads();  // every slot record of this walker is written ...
+        if (tid == 0) {
+            __threadfence();  // ... and visible before the workers see the count
+            atomicAdd(ws.counters + 4, 1);
+            trace_max(ws, 3);
+        }
         return;
     }
 

@@ -207,8 +207,8 @@ def test_direct_and_mixed_stage2_give_the_queue_paths_bits(tmp_path):
         subprocess.run([sys.executable, str(script), root, str(out)], check=True, env={**os.environ, **env})
         res[tag] = np.load(out)
     d, q = res["default"], res["queue"]
-    assert str(d["k_40_windowed"][0]) == "window_direct_kernel+eval_slots_kernel"
-    assert str(d["k_320_windowed"][0]) == "window_direct_kernel+eval_slots_kernel"
+    assert str(d["k_40_windowed"][0]) == "window_direct_kernel+window_direct_kernel(queue workers)"
+    assert str(d["k_320_windowed"][0]) == "window_direct_kernel+window_direct_kernel(queue workers)"
     assert str(d["k_1000_windowed"][0]) == "window_ranges_kernel+eval_mixed_kernel"
     assert str(d["k_320_brute"][0]) == "sweep_walkers_kernel+eval_mixed_kernel"
     assert str(d["k_40_brute"][0]) == "sweep_walkers_kernel+eval_slots_kernel"
