@@ -44,9 +44,13 @@ constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-t
 #define NMB_EVAL_MINB 5          // resident stage-2 blocks per SM of the default arithmetic (96 registers)
 #endif
 #ifndef NMB_SWEEP_MINB
-#define NMB_SWEEP_MINB 6         // resident 128-walker sweep blocks per SM (80 registers: no spills with eight timestamps per
-                                 // trip).  Measured on the 65 k x 4096 sweep (S = 15) / the 500 k x 2048 one (S = 10):
-                                 // 4 per trip at 8 blocks 0.692 ms, at 7 blocks 0.662 / 1.714, 8 per trip at 6 blocks 0.652 / 1.632
+#define NMB_SWEEP_MINB 5         // resident 128-walker sweep blocks per SM (96 registers, sixteen timestamps per trip).
+                                 // With one DFMA per fine sample (profiles/r02e2_ab_sweep_minb_trip.txt), the 65 k x 4096
+                                 // sweep (S = 15) / the 500 k x 2048 one (S = 10) / the 256-candidate batch (S = 11):
+                                 // 8 per trip at 6 blocks 0.442 / 1.190 / 0.167 ms, at 5 blocks 0.468 / 1.227 / 0.158,
+                                 // 16 per trip at 5 blocks 0.438 / 1.063 / 0.165, 4 per trip at 6 blocks 0.495 / 1.273 / 0.162.
+                                 // (ptxas schedules the S = 10 loop of the 8-per-trip build with its shared-memory loads
+                                 // issued just in time; sixteen per trip at 96 registers is the stable choice.)
 #endif
 
 // Per-stage device timing (nmb_stage_timing / nmb_stage_times): CUDA events around stage 1 and
@@ -327,10 +331,10 @@ inline int direct_cap_slots(const nmb_lc* lc, bool queue_runs_beside) {
     return (kEvalThreads / 32) * (queue_runs_beside ? std::min(per_warp, lc->ws.merge) : lc->ws.merge);
 }
 
-template <int S, int THREADS, int MINB>
+template <int S, int THREADS, int MINB, bool SUB>
 int launch_sweep_t(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                    cudaStream_t st, const nmb::SampleCtx& sc) {
-    auto kern = nmb::sweep_walkers_kernel<S, THREADS, kSweepChunk, MINB>;
+    auto kern = nmb::sweep_walkers_kernel<S, THREADS, kSweepChunk, MINB, SUB>;
     const size_t smem = sizeof(nmb::WalkSmem<S, kSweepChunk>);
     static thread_local int resident = 0;
     if (!resident) {
@@ -374,8 +378,13 @@ int launch_sweep(nmb_lc* lc, const double* params, int W, const double* priors, 
     static const int force_thr = std::getenv("NMB_SWEEP_THREADS") ? std::atoi(std::getenv("NMB_SWEEP_THREADS")) : 0;
     const long long blocks128 = (long long)lc->ncand * ((W + 127) / 128) * lc->ngran;
     const bool wide = force_thr ? (force_thr == 128) : (W >= 128 || blocks128 >= 4 * 148);
-    int rc = !wide ? launch_sweep_t<S, 32, 16>(lc, params, W, priors, lnprob, loglike, st, sc)
-                   : launch_sweep_t<S, 128, NMB_SWEEP_MINB>(lc, params, W, priors, lnprob, loglike, st, sc);
+    // a tail warp of 16 walkers or fewer (W = 100: four) takes the several-lanes-per-walker layout
+    const int tail = W % 32;
+    const bool sub = S > 0 && tail >= 1 && tail <= 16;
+    int rc = !wide ? (sub ? launch_sweep_t<S, 32, 16, true>(lc, params, W, priors, lnprob, loglike, st, sc)
+                          : launch_sweep_t<S, 32, 16, false>(lc, params, W, priors, lnprob, loglike, st, sc))
+                   : (sub ? launch_sweep_t<S, 128, NMB_SWEEP_MINB, true>(lc, params, W, priors, lnprob, loglike, st, sc)
+                          : launch_sweep_t<S, 128, NMB_SWEEP_MINB, false>(lc, params, W, priors, lnprob, loglike, st, sc));
     if (rc) return rc;
     lc->timer.mark(1, st);
     rc = mixed ? launch_mixed<S>(lc, params, W, priors, lnprob, loglike, st, sc, dtype)

@@ -205,11 +205,11 @@ __device__ __forceinline__ unsigned sweep_yand(double vs, double ti, const doubl
     return a;
 }
 #ifndef NMB_SWEEP_TRIP
-#define NMB_SWEEP_TRIP 8
+#define NMB_SWEEP_TRIP 16
 #endif
 constexpr int kSweepTrip = NMB_SWEEP_TRIP;  // timestamps per trip of the sweep's inner loop (even, divides the chunk)
 
-template <int S, int THREADS, int CH, int MINB>
+template <int S, int THREADS, int CH, int MINB, bool SUB>
 __global__ void __launch_bounds__(THREADS, MINB)
 sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gpb,
                      const double* __restrict__ priors, EvalWs ws, double* __restrict__ lnprob,
@@ -227,8 +227,24 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
     const int n = (int)lc.n[cand];
     const int g0 = tb * gpb, g1 = min(g0 + gpb, ngran);
     const int c_begin = g0 * cpg, c_end = min(g1 * cpg, (n + CH - 1) / CH);  // live chunks of this block
-    const int w = wb * THREADS + tid;
+    // Walker of this lane.  A warp whose share of the ensemble is 16 walkers or fewer (the last warp of a 100-walker
+    // ensemble holds 4) gives each walker F = 2, 4 or 8 lanes, which split the trips of a chunk between them: the
+    // classification -- all of the sweep's arithmetic -- then costs that warp 1/F of a full pass instead of a full
+    // pass for a handful of live lanes.  The walker's first lane (`leader`) still adds the chunk's terms in
+    // timestamp order, so the partial sums have the bits of the one-lane-per-walker layout.
+    // (Rotating the light warp's place in the block from block to block, so that it does not always land on the same
+    // sub-partition, was measured and loses: 0.166 -> 0.185 ms on the candidate batch.)  SUB = false compiles the
+    // one-lane-per-walker layout only: ensembles without such a tail warp run the kernel they always ran.
+    const int lane = tid & 31, wbase = wb * THREADS + (tid & ~31);
+    int F = 1;
+    if (S > 0 && SUB) {
+        const int rem = W - wbase;
+        F = (rem >= 17 || rem <= 0) ? 1 : rem >= 9 ? 2 : rem >= 5 ? 4 : 8;
+    }
+    const int sub = lane & (F - 1);
+    const int w = wbase + lane / F;
     const bool active = w < W;
+    const bool leader = active && sub == 0;
     const long long cw = (long long)cand * W + w;
     const double* __restrict__ gt = lc.t + (long long)cand * lc.npad;
     const double* __restrict__ gterm = lc.term + (long long)cand * lc.npad;
@@ -256,14 +272,14 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
             const Proposal pr = propose_compute(sc, cand, w);
 #pragma unroll
             for (int d = 0; d < 6; ++d) par[d] = pr.q[d];
-            if (tb == 0) propose_store(sc, pr, cand, w, W);
+            if (tb == 0 && sub == 0) propose_store(sc, pr, cand, w, W);
         } else {
 #pragma unroll
             for (int d = 0; d < 6; ++d) par[d] = params[cw * 6 + d];
         }
         const WalkerConsts wc = make_walker_consts(par, Sx);
         swc = make_sweep_consts(wc, span);
-        if (tb == 0) ws.wcs[cw] = wc;
+        if (tb == 0 && sub == 0) ws.wcs[cw] = wc;
     }
     __syncthreads();  // mbarrier init and offsets visible
     if (tid == 0) trace_max(ws, 1);  // constants ready
@@ -308,7 +324,45 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
             const double* src = (tid & 1 ? lc.w : lc.f) + (long long)cand * lc.npad + base + (tid >> 1) * 16;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
         }
-        if (S > 0) {
+        if (S > 0 && SUB && F > 1) {
+            // several lanes per walker: lane `sub` classifies the trips sub, sub + F, ... of the chunk and marks
+            // the timestamps that may be in transit; the marks of the walker's lanes are combined and its leader
+            // adds the other timestamps' terms in timestamp order
+            static_assert(CH <= 64, "one mark per timestamp of a chunk in a 64-bit word");
+            constexpr int NT = kSweepTrip;
+            unsigned long long mask = 0ull;
+#pragma unroll 1
+            for (int i0 = sub * NT; i0 < CH; i0 += F * NT) {
+                unsigned q[NT];
+                unsigned qall = 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    q[j] = sweep_yand<S>(vs, tr[i0 + j], ck);
+                    qall &= q[j];
+                }
+                if (!(qall & kSweepOutBit)) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+                        if (!(q[j] & kSweepOutBit)) mask |= 1ull << (i0 + j);
+                }
+            }
+            for (int o = 1; o < F; o <<= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+            if (sub == 0) {
+                if (mask == 0ull) {
+#pragma unroll 8
+                    for (int i = 0; i < CH; ++i) acc += tm[i];
+                } else {
+                    for (int i = 0; i < CH; ++i) {
+                        if ((mask >> i) & 1ull) {
+                            lo = min(lo, base + i);
+                            hi = base + i + 1;
+                        } else {
+                            acc += tm[i];
+                        }
+                    }
+                }
+            }
+        } else if (S > 0) {
             // NT timestamps per trip.  The common case -- none of them can be in transit -- costs, beside the
             // S DFMA and S / 2 logic operations per timestamp, one more AND, a bit test and a branch per
             // trip and one DADD per timestamp; the per-timestamp book-keeping runs only on the rare trips that
@@ -362,17 +416,17 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
             }
         }
         if ((c + 1) % cpg == 0 || c + 1 == c_end) {  // granule complete: publish its partial sum
-            if (active) prow[(long long)(c / cpg) * W] = acc;
+            if (leader) prow[(long long)(c / cpg) * W] = acc;
             acc = 0.0;
         }
     }
     pdl_trigger();  // stage 2 may be scheduled; it waits for this grid to finish before reading
     {   // granules of this span that lie entirely beyond the light curve
         const int gdone = (c_end > c_begin) ? (c_end + cpg - 1) / cpg : g0;
-        if (active)
+        if (leader)
             for (int g = gdone; g < g1; ++g) prow[(long long)g * W] = 0.0;
     }
-    if (active && hi > lo) {
+    if (leader && hi > lo) {
         atomicMin(ws.rlo + cw, lo);
         atomicMax(ws.rhi + cw, min(hi, n));
     }
@@ -390,9 +444,12 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
     __syncthreads();
     if (!sm.flag) return;
     __threadfence();
+    // (one walker per thread again, whatever the lane layout of the sweep was)
     int lo_w = 0, hi_w = 0;
-    if (active) {
-        const double* col = ws.partials + (long long)cand * ngran * W + w;
+    const int wf = wb * THREADS + tid;
+    const long long cwf = (long long)cand * W + wf;
+    if (wf < W) {
+        const double* col = ws.partials + (long long)cand * ngran * W + wf;
         double sacc = 0.0;
         int g = 0;
         for (; g + 16 <= ngran; g += 16) {  // sixteen loads in flight, summed in granule order
@@ -403,20 +460,20 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
             for (int j = 0; j < 16; ++j) sacc += v[j];
         }
         for (; g < ngran; ++g) sacc += __ldcg(col + (long long)g * W);
-        lo_w = __ldcg(ws.rlo + cw);
-        hi_w = __ldcg(ws.rhi + cw);
+        lo_w = __ldcg(ws.rlo + cwf);
+        hi_w = __ldcg(ws.rhi + cwf);
         if (hi_w - lo_w <= 0) {  // never in transit: done here
-            const double* par = (sc.enabled ? sc.q : params) + cw * 6;
+            const double* par = (sc.enabled ? sc.q : params) + cwf * 6;
             const double lp = priors ? ln_prior_dev(par, priors + (long long)cand * 36, 6) : 0.0;
-            finish_walker(sc, cw, W, sacc, lp, lnprob, loglike);
-            ws.rlo[cw] = INT_MAX;
-            ws.rhi[cw] = 0;
+            finish_walker(sc, cwf, W, sacc, lp, lnprob, loglike);
+            ws.rlo[cwf] = INT_MAX;
+            ws.rhi[cwf] = 0;
             lo_w = hi_w = 0;
         } else {
-            ws.oot[cw] = sacc;
+            ws.oot[cwf] = sacc;
         }
     }
-    push_slots<THREADS>(ws, cw, lo_w, hi_w, sm.s_scan);
+    push_slots<THREADS>(ws, cwf, lo_w, hi_w, sm.s_scan);
     if (tid == 0) trace_max(ws, 3);  // fold + queue push done
 }
 
@@ -1111,13 +1168,23 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
         pr_lo = __ldg(row); pr_hi = __ldg(row + 1); pr_kind = __ldg(row + 2); pr_mu = __ldg(row + 3); pr_sg = __ldg(row + 4);
     }
     const CandGeom geo = load_cand_geom(lc, cand, Sx);
-    pdl_wait();     // walker positions come from the previous kernel
+    // the random draws of the proposal and the walker's own position do not depend on the previous half-step
+    // (it updates the other half of the ensemble): both are ready when the grid dependency resolves
+    Draw dr = Draw{};
+    double s_own[kMaxDim];
+    if (sc.enabled) {
+        dr = propose_draw(sc, cand, cw % W);  // a pure function: every thread gets the same
+        const double* s = sc.pos + ((long long)cand * sc.W + dr.i) * sc.ndim;
+#pragma unroll
+        for (int d = 0; d < kMaxDim; ++d) s_own[d] = d < sc.ndim ? s[d] : 0.0;
+    }
+    pdl_wait();     // the complementary walkers' positions come from the previous kernel
     pdl_trigger();  // the next kernel may be scheduled; it waits for this grid to finish before reading
     if (tid == 0) trace_min(ws, 0);
 
     double p6[6];
     if (sc.enabled) {
-        const Proposal pr = propose_compute(sc, cand, cw % W);  // a pure function: every thread gets the same
+        const Proposal pr = propose_from(sc, cand, dr, s_own);
         if (tid == 0) propose_store(sc, pr, cand, cw % W, W);
 #pragma unroll
         for (int d = 0; d < 6; ++d) p6[d] = pr.q[d];

@@ -64,7 +64,14 @@ struct Proposal {
     double q[kMaxDim];
     double zz, u_a;
 };
-__device__ __forceinline__ Proposal propose_compute(const SampleCtx& sc, int cand, int k) {
+// The part of a proposal that does not depend on the ensemble's state: the stretch factor, the row of the
+// complementary walker and the acceptance draw.  A kernel may compute it before its grid dependency resolves.
+struct Draw {
+    double zz, u_a;
+    int i;    // walker being updated (index within the candidate's ensemble)
+    int jc;   // complementary walker (index within the candidate's ensemble)
+};
+__device__ __forceinline__ Draw propose_draw(const SampleCtx& sc, int cand, int k) {
     const int halfk = sc.W / 2;
     const int nS0 = sc.half == 0 ? halfk : sc.W - halfk;
     const int nS1 = sc.W - nS0;
@@ -77,18 +84,31 @@ __device__ __forceinline__ Proposal propose_compute(const SampleCtx& sc, int can
     philox4x32_10((uint32_t)sc.step, (uint32_t)(sc.step >> 32), (walker << 1) | (uint32_t)sc.half, (cnd << 1) | 1u,
                   (uint32_t)sc.seed, (uint32_t)(sc.seed >> 32), r2);
     const double u_z = u01_53(r[0], r[1]), u_j = u01_53(r[2], r[3]);
-    Proposal pr;
-    pr.u_a = u01_53(r2[0], r2[1]);
+    Draw dr;
+    dr.u_a = u01_53(r2[0], r2[1]);
     const double t = (sc.a - 1.) * u_z + 1;
-    pr.zz = t * t / sc.a;
+    dr.zz = t * t / sc.a;
     int j = (int)(u_j * (double)nS1);
     if (j >= nS1) j = nS1 - 1;
-    const double* s = sc.pos + ((long long)cand * sc.W + i) * sc.ndim;
-    const double* c = sc.pos + ((long long)cand * sc.W + c_base + j) * sc.ndim;
+    dr.i = i;
+    dr.jc = c_base + j;
+    return dr;
+}
+// `s` = the walker's current position (rows of the half being updated do not change during the previous
+// half-step, so a caller may have loaded it early); the complementary row is read here.
+__device__ __forceinline__ Proposal propose_from(const SampleCtx& sc, int cand, const Draw& dr, const double* s) {
+    Proposal pr;
+    pr.u_a = dr.u_a;
+    pr.zz = dr.zz;
+    const double* c = sc.pos + ((long long)cand * sc.W + dr.jc) * sc.ndim;
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d)
         if (d < sc.ndim) pr.q[d] = c[d] - pr.zz * (c[d] - s[d]);
     return pr;
+}
+__device__ __forceinline__ Proposal propose_compute(const SampleCtx& sc, int cand, int k) {
+    const Draw dr = propose_draw(sc, cand, k);
+    return propose_from(sc, cand, dr, sc.pos + ((long long)cand * sc.W + dr.i) * sc.ndim);
 }
 __device__ __forceinline__ void propose_store(const SampleCtx& sc, const Proposal& pr, int cand, int k, int Weval) {
     const long long e = (long long)cand * Weval + k;
