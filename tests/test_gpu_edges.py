@@ -219,3 +219,27 @@ def test_direct_and_mixed_stage2_give_the_queue_paths_bits(tmp_path):
             continue
         assert np.array_equal(d[key], q[key], equal_nan=True), key
         assert np.isfinite(d[key]).all()
+
+
+@pytest.mark.parametrize("W", [3, 37, 41, 100, 132])
+def test_sweep_tail_warp_layout_has_the_one_lane_bits(nb, W):
+    """The brute-force sweep gives the walkers of a short tail warp (W mod 32 <= 16) several lanes each
+    (csrc/eval_pipeline.cuh, `SUB`).  The same walkers inside an ensemble without such a tail (padded to a multiple
+    of 32 with copies) take the one-lane-per-walker layout and must get the same bits; both agree with the oracle."""
+    from oracle import namaste_oracle as o
+    g = load_golden("synth_k2_s11")
+    rng = np.random.default_rng(W)
+    pos = g["walkers"][0][None, :] * (1 + 2e-3 * rng.standard_normal((W, 6)))
+    pos[: max(1, W // 10), 2] *= 0.2                      # slow walkers: long in-transit ranges
+    pos[W // 2, 1] = 1.2                                   # never in transit
+    padded = np.vstack([pos, np.repeat(pos[:1], (-W) % 32 or 32, axis=0)])
+    assert len(padded) % 32 == 0
+    lc = nb.LightCurve(g["lc"], oversamp=int(g["oversamp"]))
+    tail = lc.lnprob(pos, g["priors"], mode="brute")
+    full = lc.lnprob(padded, g["priors"], mode="brute")[:W]
+    assert np.array_equal(tail, full)
+    pri = priors_from_table(g["priors"])
+    with np.errstate(all="ignore"):
+        ref = np.array([o.mono_only_logprob(p, g["lc"], pri, int(g["oversamp"])) for p in pos[:6]])
+    assert rel(tail[:6], ref).max() < 1e-11
+    lc.close()
