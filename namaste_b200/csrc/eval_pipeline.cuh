@@ -770,7 +770,14 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const int bid, const L
     // warp, prefers two slots per pass and fetched chunks.  Results do not depend on either (see SlotRec).
     const int merge = per <= 8 ? min(kEvalMerge, ws.merge + 1) : ws.merge;
     const int chunk = per <= 2 * merge ? max(1, per) : max(merge, total / (nwarps * 8));
-    const int nchunks = (total + chunk - 1) / chunk;
+    // The static deal is balanced: every warp takes floor(total / nwarps) slots and the first total mod nwarps warps
+    // one more (the warp index runs over the SMs first, so the extra slots spread over the GPU), instead of
+    // ceil(total / nwarps) slots for as many warps as it takes: with 4.15 slots per warp -- the 2048-walker half-steps
+    // of the 65 k-point light curve -- no sub-partition carries five warps of five slots while others idle.
+    // (eval_mixed_kernel's workers, PACKED, keep the block-after-block deal: their aim is to leave blocks free.)
+    const bool balanced = !PACKED && per <= 2 * merge;
+    const int base = total / nwarps, extra = total - base * nwarps;
+    const int nchunks = balanced ? min(total, nwarps) : (total + chunk - 1) / chunk;
     int* queue = ws.counters + 2;
     int ch_cur = gw, ch_nxt = INT_MAX;
     if (nchunks > nwarps) {
@@ -815,7 +822,8 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const int bid, const L
 
     if (lane == 0) trace_max(ws, 9);
     while (ch_cur < nchunks) {
-      const int s0 = ch_cur * chunk, s1 = min(total, s0 + chunk);
+      const int s0 = balanced ? ch_cur * base + min(ch_cur, extra) : ch_cur * chunk;
+      const int s1 = balanced ? s0 + base + (ch_cur < extra ? 1 : 0) : min(total, s0 + chunk);
       int ch_nn = INT_MAX;
       if (lane == 0 && ch_nxt < nchunks) ch_nn = nwarps + atomicAdd(queue, 1);
       int s = s0;
