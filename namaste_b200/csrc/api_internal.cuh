@@ -307,17 +307,18 @@ int launch_mixed(nmb_lc* lc, const double* params, int W, const double* priors, 
     return launch_mixed_mb<S, NMB_EVAL_MINB, 3>(lc, params, W, priors, lnprob, loglike, st, sc);
 }
 
-// Ensembles between a few hundred walkers and about two resident waves of direct blocks take the mixed
-// stage 2: short ranges are evaluated by a block per walker, only long ranges are queued.  Below that the
-// queue alone already gives every slot its own warp (config 1, 100 walkers: 30.7 us against 34.7 us mixed);
-// above it the queue balances better than waves of blocks.  Measured on config 2 (1024 walkers) against the
-// queue alone: repeated evaluations on a warm L2 (the sampler, host-API calls) gain -- MCMC 12.8 k -> 14.0 k
-// steps/s brute force, e2e 5.4e10 -> 5.8e10 wt/s, windowed step 46.0 -> 44.2 us -- while a brute-force step
-// on a flushed L2 loses 2.6 us (49.9 -> 52.5 us: three waves of direct blocks, each paying its cold misses).
-// NMB_MIXED_MINCW / NMB_MIXED_MAXCW override.
+// The mixed stage 2 (eval_mixed_kernel: short ranges evaluated by a block per walker, only long ranges queued) was
+// the default for ensembles of 256 ... 1184 walkers until the queue's short-queue deal (three slots per pass, static
+// and balanced, eval_slots_body) and the queue workers inside window_direct_kernel arrived.  Measured again on the
+// K2-like light curve (profiles/r02h2_scale_mixed_vs_queue.txt; back-to-back / L2 flushed, us):
+//   windowed  768 walkers: mixed 30.4 / 37.9, queue 26.1 / 31.8;  1024: 34.3 / 43.1 against 32.3 / 38.9
+//   brute     512 walkers: mixed 28.6 / 35.8, queue 29.0 / 33.8;  1024: 38.2 / 48.2 against 40.0 / 46.1
+// The queue wins everywhere on a flushed L2 and in windowed mode; the mixed kernel keeps 2 us on back-to-back
+// brute-force evaluations of ~1000 walkers, which is not a product path.  It is therefore off by default and kept
+// behind NMB_MIXED_MINCW / NMB_MIXED_MAXCW (tests/test_gpu_edges.py runs it and compares its bits).
 inline bool use_mixed(const nmb_lc* lc, size_t CW) {
     static const long long lo = std::getenv("NMB_MIXED_MINCW") ? std::atoll(std::getenv("NMB_MIXED_MINCW")) : 256;
-    static const long long hi = std::getenv("NMB_MIXED_MAXCW") ? std::atoll(std::getenv("NMB_MIXED_MAXCW")) : 1184;
+    static const long long hi = std::getenv("NMB_MIXED_MAXCW") ? std::atoll(std::getenv("NMB_MIXED_MAXCW")) : 0;
     return !lc->ws.modelbuf && (long long)CW >= lo && (long long)CW <= hi;
 }
 

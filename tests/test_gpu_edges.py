@@ -194,26 +194,32 @@ np.savez(sys.argv[2], **out)
 
 
 def test_direct_and_mixed_stage2_give_the_queue_paths_bits(tmp_path):
-    """window_direct_kernel / eval_mixed_kernel (block per walker) against the pure queue pipeline
-    (NMB_DIRECT=0, NMB_MIXED_MAXCW=0 in a second process): identical bits for every walker, mode and
-    arithmetic, on ensembles that take each of the paths."""
+    """window_direct_kernel (block per walker, the default for small ensembles) and eval_mixed_kernel (switched on
+    with NMB_MIXED_* in a third process) against the pure queue pipeline (NMB_DIRECT=0, NMB_MIXED_MAXCW=0 in a second
+    process): identical bits for every walker, mode and arithmetic, on ensembles that take each of the paths."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "paths.py"
     script.write_text(_PATH_SCRIPT)
     res = {}
-    for tag, env in (("default", {}), ("queue", {"NMB_DIRECT": "0", "NMB_MIXED_MAXCW": "0"})):
+    for tag, env in (("default", {}), ("queue", {"NMB_DIRECT": "0", "NMB_MIXED_MAXCW": "0"}),
+                     ("mixed", {"NMB_MIXED_MINCW": "256", "NMB_MIXED_MAXCW": "1184"})):
         out = tmp_path / (tag + ".npz")
         subprocess.run([sys.executable, str(script), root, str(out)], check=True, env={**os.environ, **env})
         res[tag] = np.load(out)
-    d, q = res["default"], res["queue"]
+    d, q, m = res["default"], res["queue"], res["mixed"]
     assert str(d["k_40_windowed"][0]) == "window_direct_kernel+window_direct_kernel(queue workers)"
     assert str(d["k_320_windowed"][0]) == "window_direct_kernel+window_direct_kernel(queue workers)"
-    assert str(d["k_1000_windowed"][0]) == "window_ranges_kernel+eval_mixed_kernel"
-    assert str(d["k_320_brute"][0]) == "sweep_walkers_kernel+eval_mixed_kernel"
+    assert str(d["k_1000_windowed"][0]) == "window_ranges_kernel+eval_slots_kernel"
+    assert str(d["k_320_brute"][0]) == "sweep_walkers_kernel+eval_slots_kernel"
     assert str(d["k_40_brute"][0]) == "sweep_walkers_kernel+eval_slots_kernel"
+    assert str(m["k_1000_windowed"][0]) == "window_ranges_kernel+eval_mixed_kernel"
+    assert str(m["k_320_brute"][0]) == "sweep_walkers_kernel+eval_mixed_kernel"
     for k in ("k_40_windowed", "k_320_windowed", "k_1000_windowed", "k_320_brute"):
         assert str(q[k][0]).endswith("eval_slots_kernel") and "direct" not in str(q[k][0])
+    for key in m.files:
+        if not key.startswith("k_"):
+            assert np.array_equal(m[key], q[key], equal_nan=True), ("mixed", key)
     for key in d.files:
         if key.startswith("k_"):
             continue
