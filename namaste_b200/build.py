@@ -72,6 +72,8 @@ def build_library(force=False, verbose=False, extra_flags=(), out=None, sources=
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     os.replace(tmp, lib)
+    if variant:
+        shutil.rmtree(objdir, ignore_errors=True)   # keep the tree small: the snapshot sent to the GPU box is size-limited
     return lib
 
 

@@ -58,7 +58,8 @@ struct EvalWs {
     double* slotpart;    // [slotcap]  chi^2 partial of each slot
     int* slotsdone;      // [CW]  (0 when idle)
     int* grouptick;      // [C*walker blocks] finished time blocks per walker group (0 when idle)
-    int* counters;       // [4] direct blocks of window_direct_kernel that have decided (evaluate / finish / queue);
+    int* counters;       // [5] set when a pushed walker has slots of several passes (non-uniform queue);
+                         // [4] direct blocks of window_direct_kernel that have decided (evaluate / finish / queue);
                          // [1] slots pushed by stage 1 (queue tail), [2] next dynamically assigned chunk,
                          // [3] stage-2 blocks finished; the last stage-2 block zeroes them
     int maxslots;        // slots per walker are capped; longer ranges put several passes in a slot
@@ -117,6 +118,7 @@ __device__ __forceinline__ void push_slots(const EvalWs& ws, long long cw, int l
     int pps;
     int mine = slots_for(hi - lo, ws.tsw, ws.maxslots, pps);
     if (pps == 1 && mine <= ws.direct_cap) mine = 0;  // left to a direct block of eval_mixed_kernel
+    if (pps > 1) atomicOr(ws.counters + 5, 1);  // slots of several passes: the queue is not homogeneous (rare)
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -775,7 +777,18 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const int bid, const L
     // ceil(total / nwarps) slots for as many warps as it takes: with 4.15 slots per warp -- the 2048-walker half-steps
     // of the 65 k-point light curve -- no sub-partition carries five warps of five slots while others idle.
     // (eval_mixed_kernel's workers, PACKED, keep the block-after-block deal: their aim is to leave blocks free.)
-    const bool balanced = !PACKED && per <= 2 * merge;
+#ifndef NMB_STATIC_MAX_PER
+#define NMB_STATIC_MAX_PER 24
+#endif
+    // A longer queue -- up to 24 slots per warp -- is dealt statically too while every slot is a single pass (stage 1
+    // raises counters[5] when it pushes a walker whose range exceeds the per-walker slot cap: slots of several
+    // passes, very unequal work).  A warp then stays with one or two walkers (constants, completion count) and
+    // fetches nothing.  Measured (profiles/r02i2_ab_stage2_static_uniform.txt): half-step of a 1024-walker share of
+    // the 500 k-point light curve 137 -> 130 us, of the 256-candidate batch 179 -> 169 us; at 50 slots per warp (the
+    // batch's full evaluation, candidates of unequal cost) the static deal loses 8 %, and with the prior-box walkers'
+    // multi-pass slots it loses 20-60 %, hence the two conditions.
+    const bool uniform = __ldcg(ws.counters + 5) == 0;
+    const bool balanced = !PACKED && (per <= 2 * merge || (uniform && per <= NMB_STATIC_MAX_PER));
     const int base = total / nwarps, extra = total - base * nwarps;
     const int nchunks = balanced ? min(total, nwarps) : (total + chunk - 1) / chunk;
     int* queue = ws.counters + 2;
@@ -965,6 +978,7 @@ eval_slots_body(EvalSmem<THREADS>& sm, const int nblocks, const int bid, const L
             ws.counters[2] = 0;
             ws.counters[3] = 0;
             ws.counters[4] = 0;
+            ws.counters[5] = 0;
         }
     }
 }
@@ -1235,6 +1249,7 @@ window_direct_kernel(LcView lc, const double* __restrict__ params, int W, const 
     }
     if (queued) {  // too long for one block: onto the queue
         if (tid == 0) {
+            if (pps > 1) atomicOr(ws.counters + 5, 1);
             sm.first = atomicAdd(ws.counters + 1, nsl);
             ws.oot[cw] = oot_words.value();
             ws.wcs[cw] = wcr;
