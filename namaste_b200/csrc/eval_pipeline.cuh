@@ -567,6 +567,19 @@ __device__ __forceinline__ void walker_range(const LcView& lc, int cand, const W
         ilo = __ldg(grid + j0);
         ihi = (jh > (double)gc) ? n : __ldg(grid + j1);
         if (ihi < ilo) ihi = ilo;
+#ifndef NMB_NO_WINDOW_TRIM
+        // The cell lookup lands one to two cadences outside [tlo, thi] on either side: three timestamps of ~30 whose
+        // samples all leave the flux function at once but still take lanes in the first and last rounds of the range.
+        // A timestamp has a sample inside the window only if tlo <= t_i <= thi (tlo already carries the span of the
+        // supersampling offsets), so up to two timestamps per side are dropped by looking at their times.
+        if (ihi - ilo >= 4) {
+            const double* __restrict__ tt = lc.t + (long long)cand * lc.npad;
+            const double a0 = __ldg(tt + ilo), a1 = __ldg(tt + ilo + 1);
+            const double b0 = __ldg(tt + ihi - 1), b1 = __ldg(tt + ihi - 2);
+            if (a0 < tlo) ilo += (a1 < tlo) ? 2 : 1;
+            if (b0 > thi) ihi -= (b1 > thi) ? 2 : 1;
+        }
+#endif
     }
 }
 __device__ __forceinline__ void walker_window(const LcView& lc, int cand, const WalkerConsts& wc, const CandGeom& geo,
