@@ -24,7 +24,7 @@ extern "C" void nmb_lc_destroy(nmb_lc* lc) {
     cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_term); cudaFree(lc->d_var); cudaFree(lc->d_modelbuf); cudaFree(lc->d_meanpar); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
     cudaFree(lc->d_tgrid); cudaFree(lc->d_gcount); cudaFree(lc->d_t0); cudaFree(lc->d_ginv);
     cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
-    cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.wcs); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
+    cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.wcs); cudaFree(lc->ws.swc); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
     cudaFree(lc->ws.nslots); cudaFree(lc->ws.slots); cudaFree(lc->ws.slotpart); cudaFree(lc->ws.slotsdone);
     cudaFree(lc->ws.grouptick); cudaFree(lc->ws.counters); cudaFree(lc->ws.trace);
     if (lc->h_pin) cudaFreeHost(lc->h_pin);

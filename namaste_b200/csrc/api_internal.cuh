@@ -190,7 +190,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 inline int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
     nmb::EvalWs& ws = lc->ws;
     if (CW > lc->ws_cw) {
-        cudaFree(ws.oot); cudaFree(ws.wcs); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.nslots);
+        cudaFree(ws.oot); cudaFree(ws.wcs); cudaFree(ws.swc); cudaFree(ws.rlo); cudaFree(ws.rhi); cudaFree(ws.nslots);
         cudaFree(ws.slots); cudaFree(ws.slotpart); cudaFree(ws.slotsdone); cudaFree(ws.grouptick);
         cudaFree(ws.counters); cudaFree(ws.trace);
         cudaFree(ws.partials);
@@ -208,6 +208,7 @@ inline int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
         const size_t cap = CW * ws.maxslots;
         CU(cudaMalloc(&ws.oot, CW * sizeof(double)));
         CU(cudaMalloc(&ws.wcs, CW * sizeof(nmb::WalkerConsts)));
+        CU(cudaMalloc(&ws.swc, CW * sizeof(nmb::SweepConsts)));
         CU(cudaMalloc(&ws.rlo, CW * sizeof(int)));
         CU(cudaMalloc(&ws.rhi, CW * sizeof(int)));
         CU(cudaMalloc(&ws.slotsdone, CW * sizeof(int)));
@@ -348,7 +349,6 @@ int launch_sweep_t(nmb_lc* lc, const double* params, int W, const double* priors
         resident = sms * std::max(per_sm, 1);
     }
     const size_t CW = (size_t)lc->ncand * W;
-    (void)CW;
     const int nwb = (W + THREADS - 1) / THREADS;
     // granules per block: many more blocks than resident slots, so that the hardware block scheduler
     // evens out the SMs (measured: 5-8 % faster than one exactly-resident wave on the 65 k and 500 k
@@ -362,8 +362,17 @@ int launch_sweep_t(nmb_lc* lc, const double* params, int W, const double* priors
     gpb = std::min(gpb, lc->ngran);
     const int ntb = (lc->ngran + gpb - 1) / gpb;
     dim3 grid(ntb, nwb, (unsigned)lc->ncand);
+    // walker groups swept by many time blocks: the walkers' constants are derived once, by a kernel in front
+    static const int pre_min = std::getenv("NMB_SWEEP_PRE_MIN") ? std::atoi(std::getenv("NMB_SWEEP_PRE_MIN")) : 16;
+    lc->ws.pre_consts = (pre_min > 0 && ntb >= pre_min) ? 1 : 0;
+    if (lc->ws.pre_consts) {
+        CU(launch_pdl(nmb::sweep_consts_kernel, dim3((unsigned)((CW + 127) / 128)), dim3(128), 0, st, lc->view(), params, W,
+                      lc->ws, sc));
+        g_launches++;
+    }
     CU(launch_pdl(kern, grid, dim3(THREADS), smem, st, lc->view(), params, W, gpb, priors, lc->ws, lnprob, loglike, sc));
     g_launches++;
+    lc->ws.pre_consts = 0;
     return NMB_OK;
 }
 

@@ -51,6 +51,8 @@ struct EvalWs {
     double* partials;    // [C][ngran][W]  out-of-transit chi^2 per (granule, walker)   (brute)
     double* oot;         // [CW]           out-of-transit chi^2 per walker
     WalkerConsts* wcs;   // [CW]
+    SweepConsts* swc;    // [CW]  classification constants of the brute-force sweep, when sweep_consts_kernel ran first
+    int pre_consts;      // 1: the sweep's blocks load swc instead of deriving the walker's constants themselves
     int* rlo;            // [CW]  first in-transit timestamp   (INT_MAX when idle)
     int* rhi;            // [CW]  one past the last            (0 when idle)
     int* nslots;         // [CW]  slots of each walker with work in stage 2
@@ -211,6 +213,34 @@ __device__ __forceinline__ unsigned sweep_yand(double vs, double ti, const doubl
 #endif
 constexpr int kSweepTrip = NMB_SWEEP_TRIP;  // timestamps per trip of the sweep's inner loop (even, divides the chunk)
 
+// One thread per walker: proposal (sampler), model constants and the sweep's classification constants, once, for
+// ensembles whose walker groups are swept by many time blocks (launched in front of sweep_walkers_kernel).
+static __global__ void __launch_bounds__(128)
+sweep_consts_kernel(LcView lc, const double* __restrict__ params, int W, EvalWs ws, SampleCtx sc) {
+    const long long cw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Sx = lc.S;
+    const bool active = cw < (long long)W * lc.ncand;
+    const int cand = active ? (int)(cw / W) : 0, w = active ? (int)(cw % W) : 0;
+    const double span = lc.off[(long long)cand * Sx + Sx - 1];
+    pdl_wait();     // walker positions come from the previous kernel
+    pdl_trigger();  // the sweep may be scheduled; it waits for this grid to finish before reading
+    if (!active) return;
+    double par[6];
+    if (sc.enabled) {
+        const Proposal pr = propose_compute(sc, cand, w);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) par[d] = pr.q[d];
+        propose_store(sc, pr, cand, w, W);
+    } else {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) par[d] = params[cw * 6 + d];
+    }
+    const WalkerConsts wc = make_walker_consts(par, Sx);
+    ws.wcs[cw] = wc;
+    const SweepConsts c = make_sweep_consts(wc, span);
+    ws.swc[cw] = c;
+}
+
 template <int S, int THREADS, int CH, int MINB, bool SUB>
 __global__ void __launch_bounds__(THREADS, MINB)
 sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gpb,
@@ -268,7 +298,13 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
     // what stage 2 and the finalisation need: proposal and model constants)
     SweepConsts swc = {0.0, 4.0, 1.0, 0.0};  // padding lanes never hit
     const double span = lc.off[(long long)cand * Sx + Sx - 1];  // staged light curve: read before the grid dependency
-    if (active) {
+    if (active && ws.pre_consts) {
+        // many time blocks per walker group: sweep_consts_kernel derived the constants once (32 B per walker to load
+        // here instead of a chain of ~150 FP64 instructions that queues behind the other warps' DFMA streams)
+        const double2 v0 = __ldcg(reinterpret_cast<const double2*>(ws.swc + cw));
+        const double2 v1 = __ldcg(reinterpret_cast<const double2*>(ws.swc + cw) + 1);
+        swc.vel = v0.x; swc.nvtc = v0.y; swc.s = v1.x; swc.vs = v1.y;
+    } else if (active) {
         double par[6];
         if (sc.enabled) {
             const Proposal pr = propose_compute(sc, cand, w);

@@ -67,7 +67,7 @@ struct WalkerConsts {
 //   X = (Xq + kEps (4 |vel tcen| + 2 |vel| span)) (1 + 64 kEps) exceeds Xq by more than that, and s is rounded
 //   down so that {|y| < 2} contains {|vx| <= X}: the window is a superset of the reference's in-transit samples.
 // Samples inside the window are not assumed to be in transit -- stage 2 classifies them faithfully.
-struct SweepConsts {
+struct alignas(32) SweepConsts {
     double vel, nvtc, s, vs;   // c_k = fma(vel, off_k, nvtc) * s,  V = vs
 };
 constexpr unsigned kSweepOutBit = 0x40000000u;   // set in hi32(y)  <=>  |y| >= 2 (or y not finite)
