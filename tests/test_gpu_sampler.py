@@ -42,6 +42,24 @@ def test_chain_matches_cpu_oracle_draw_by_draw(nb, mode):
     assert 0.1 < s.acceptance_fraction.mean() < 0.9
 
 
+def test_chain_with_queued_walkers_matches_cpu_oracle(nb):
+    """Slow walkers in the initial ensemble (long in-transit ranges) leave window_direct_kernel's direct blocks for
+    the slot queue, which the queue workers at the end of the same launch drain: accept / reject of those walkers
+    runs in the workers.  The chain must still be the CPU oracle's, draw by draw."""
+    from oracle import namaste_oracle as o, stretch_oracle as so
+    lc, pri, pos0 = _problem()
+    pos0 = pos0.copy()
+    pos0[::5, 2] *= 0.04            # five walkers ~25x slower: a few hundred timestamps in transit
+    nsteps, seed = 12, 77
+    with np.errstate(all="ignore"):
+        ref_chain, ref_ln, ref_acc = so.run(lambda p: o.lnprob_ensemble(p, lc, pri), pos0, nsteps, seed)
+    s = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri, nb.MonotransitModel(*pos0[0])), seed=seed)
+    s.run_mcmc(pos0, nsteps)
+    assert np.array_equal(s.chain, ref_chain)
+    assert np.allclose(s.lnprobability, ref_ln, rtol=1e-11, atol=0)
+    assert np.array_equal(s.naccepted, ref_acc)
+
+
 def test_run_mcmc_appends_and_reset(nb):
     lc, pri, pos0 = _problem()
     s = nb.EnsembleSampler(24, 6, nb.MonoOnlyLogProb, args=(lc, pri), seed=7)
