@@ -94,8 +94,10 @@ int nmb_lc_oversamp(const nmb_lc* lc);
 int nmb_lnprob(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob, double* loglike,
                int mode, int dtype, void* stream);
 
-/* Same with HOST buffers: copies params (and priors) to the device through pinned staging,
- * launches, copies lnprob (and loglike if non-NULL) back and synchronises. */
+/* Same with HOST buffers: copies params (and priors) to the device, launches, copies lnprob (and loglike if
+ * non-NULL) back and synchronises.  Ordinary host memory passes through the handle's pinned staging buffer; a
+ * `params` / `lnprob` (+ `loglike`) buffer that is itself page-locked (cudaMallocHost, cudaHostRegister) is copied
+ * to / from the device directly. */
 int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob, double* loglike,
                     int mode, int dtype);
 

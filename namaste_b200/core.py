@@ -89,9 +89,13 @@ class LightCurve:
             pass
 
     # ---- host-buffer path (the call a reference user makes) --------------------------------
-    def lnprob(self, params, priors=None, mode="windowed", return_loglike=False, dtype="f64"):
+    def lnprob(self, params, priors=None, mode="windowed", return_loglike=False, dtype="f64", out=None):
         """Ensemble log-probability.  ``params`` is [W, 6] (single light curve) or
-        [ncand, W, 6]; returns [W] / [ncand, W] (and the bare log-likelihood if asked)."""
+        [ncand, W, 6]; returns [W] / [ncand, W] (and the bare log-likelihood if asked).
+
+        ``out``: optional float64 C-contiguous array of the result's shape to write into.  Buffers in page-locked
+        host memory (e.g. ``torch.empty(..., pin_memory=True).numpy()``) -- ``params`` and / or ``out`` -- are copied
+        to and from the device directly; ordinary arrays pass through the handle's pinned staging buffer."""
         lib = load()
         p = as_f64(params)
         squeeze = p.ndim == 2
@@ -108,7 +112,13 @@ class LightCurve:
                 tab = tab.reshape(self.ncand, 6, 6)
             else:
                 tab = np.ascontiguousarray(np.broadcast_to(tab, (self.ncand, 6, 6)))
-        out = np.empty((self.ncand, W))
+        if out is None:
+            out = np.empty((self.ncand, W))
+        else:
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous
+                    and out.size == self.ncand * W):
+                raise ValueError("out must be a C-contiguous float64 array with ncand * W elements")
+            out = out.reshape(self.ncand, W)
         ll = np.empty((self.ncand, W)) if return_loglike else None
         check(lib.nmb_lnprob_host(self._h, ptr(p), W, ptr(tab), ptr(out), ptr(ll), MODES[mode], DTYPES[dtype]), "lnprob")
         if squeeze:

@@ -224,6 +224,17 @@ extern "C" int nmb_lnprob(nmb_lc* lc, const double* params, int64_t W, const dou
     return lnprob_impl(lc, params, W, priors, lnprob, loglike, mode, dtype, stream, sc);
 }
 
+// true for page-locked host memory (cudaMallocHost / cudaHostRegister / torch pin_memory): such a buffer is copied
+// to or from the device directly, without the handle's staging buffer in between
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, const double* priors, double* lnprob,
                                double* loglike, int mode, int dtype) {
     if (!lc || !params || !lnprob) return fail(NMB_ERR_ARG, "nmb_lnprob_host: null pointer");
@@ -241,13 +252,29 @@ extern "C" int nmb_lnprob_host(nmb_lc* lc, const double* params, int64_t W, cons
         lc->pin_cap = total;
     }
     cudaStream_t st = lc->own_stream;
-    std::memcpy(lc->h_pin, params, np * sizeof(double));
-    if (priors) std::memcpy(lc->h_pin + np, priors, npri * sizeof(double));
-    CU(cudaMemcpyAsync(lc->d_stage, lc->h_pin, (np + npri) * sizeof(double), cudaMemcpyHostToDevice, st));
+    // walker positions: straight from the caller's buffer when it is page-locked, through the staging buffer otherwise
+    const bool p_pinned = host_is_pinned(params);
+    const bool o_pinned = host_is_pinned(lnprob) && (!loglike || host_is_pinned(loglike));
+    if (p_pinned) {
+        CU(cudaMemcpyAsync(lc->d_stage, params, np * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        std::memcpy(lc->h_pin, params, np * sizeof(double));
+        CU(cudaMemcpyAsync(lc->d_stage, lc->h_pin, np * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (priors) {
+        std::memcpy(lc->h_pin + np, priors, npri * sizeof(double));
+        CU(cudaMemcpyAsync(lc->d_stage + np, lc->h_pin + np, npri * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     double* d_out = lc->d_stage + np + npri;
     int rc = nmb_lnprob(lc, lc->d_stage, W, priors ? lc->d_stage + np : nullptr, d_out,
                         loglike ? d_out + C * W : nullptr, mode, dtype, st);
     if (rc) return rc;
+    if (o_pinned) {
+        CU(cudaMemcpyAsync(lnprob, d_out, C * W * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (loglike) CU(cudaMemcpyAsync(loglike, d_out + C * W, C * W * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return NMB_OK;
+    }
     CU(cudaMemcpyAsync(lc->h_pin + np + npri, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     std::memcpy(lnprob, lc->h_pin + np + npri, C * W * sizeof(double));

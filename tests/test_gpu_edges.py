@@ -249,3 +249,26 @@ def test_sweep_tail_warp_layout_has_the_one_lane_bits(nb, W):
         ref = np.array([o.mono_only_logprob(p, g["lc"], pri, int(g["oversamp"])) for p in pos[:6]])
     assert rel(tail[:6], ref).max() < 1e-11
     lc.close()
+
+
+def test_lnprob_host_with_pinned_buffers_and_out(nb):
+    """nmb_lnprob_host copies page-locked caller buffers to and from the device directly and ordinary ones through
+    its staging buffer; `out=` writes into the caller's array.  Same bits every way."""
+    import torch
+    g = load_golden("synth_k2_s11")
+    lc = nb.LightCurve(g["lc"], oversamp=int(g["oversamp"]))
+    pos = np.ascontiguousarray(g["walkers"][:48])
+    ref, ref_ll = lc.lnprob(pos, g["priors"], return_loglike=True)
+    pin_in = torch.from_numpy(pos.copy()).pin_memory()
+    pin_out = torch.empty(48, dtype=torch.float64).pin_memory()
+    got = lc.lnprob(pin_in.numpy(), g["priors"], out=pin_out.numpy())
+    assert np.array_equal(got, ref) and np.array_equal(pin_out.numpy(), ref)
+    got2, ll2 = lc.lnprob(pin_in.numpy(), g["priors"], return_loglike=True, out=pin_out.numpy())   # pinned lnprob, pageable loglike
+    assert np.array_equal(got2, ref) and np.array_equal(ll2, ref_ll)
+    plain = np.empty(48)
+    assert np.array_equal(lc.lnprob(pos, g["priors"], out=plain), ref) and np.array_equal(plain, ref)
+    with pytest.raises(ValueError):
+        lc.lnprob(pos, g["priors"], out=np.empty(3))
+    with pytest.raises(ValueError):
+        lc.lnprob(pos, g["priors"], out=np.empty(48, dtype=np.float32))
+    lc.close()
