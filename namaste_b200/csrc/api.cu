@@ -1003,6 +1003,16 @@ extern "C" int nmb_sampler_run_split(nmb_sampler* s, int64_t nsteps, int store_a
     static const double tmo_s = std::getenv("NMB_SPLIT_TIMEOUT_S") ? std::atof(std::getenv("NMB_SPLIT_TIMEOUT_S")) : 10.0;
     const unsigned long long timeout_ns = (unsigned long long)(tmo_s * 1e9);
     const int xblocks = (int)std::max<int64_t>(1, std::min<int64_t>(32, (nk * s->ndim + 1023) / 1024));
+    if (world > 1) {
+        // Handshake before the first half-step: an exchange without rows.  Every rank's replica is in its initial
+        // state (set_state's copy and its evaluation of the initial lnprob precede this kernel in the stream)
+        // before any peer stores a row into it; without it a rank that is a half-step ahead could have its rows
+        // overwritten by a slower rank's own initialisation.
+        const int epoch = (int)(++s->split_epoch);
+        CU(launch_pdl(nmb::split_exchange_kernel, dim3(1), dim3(256), 0, s->st, pp, (const double*)s->d_pos,
+                      (const double*)s->d_lnp, s->ndim, 0LL, 0, epoch, s->d_flags, timeout_ns));
+        g_launches++;
+    }
     for (int64_t i = 0; i < nsteps; ++i) {
         for (int half = 0; half < 2; ++half) {
             const nmb::SampleCtx sc = sampler_ctx(s, half, (int)k0, 0);
