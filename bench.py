@@ -583,7 +583,7 @@ def roofline_of(b, wl, res, peak_tf, traffic):
                     "tools/micro/sweep_mix.cu)"}
 
 
-def measure_split(b, n_steps=20, n_check=3):
+def measure_split(b, n_steps=40, n_check=3):
     """BASELINE configs[4]: one 16384-walker ensemble on the 500 k-point light curve, split by walker over
     the ranks (the whole ensemble on one GPU at N = 1).  The split chain is compared bit for bit with a
     single-GPU run of the same seed inside the leg (rank 0), and the replicas are compared across ranks."""
