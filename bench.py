@@ -539,6 +539,22 @@ def measure_mcmc(b, wl, staged, n_mcmc, modes=("windowed", "brute")):
         out[mode] = {"steps_per_s": n_mcmc / dt, "candidate_steps_per_s": n_mcmc * C * b.world / dt,
                      "wt_per_s": n_mcmc * C * W * N * b.world / dt, "acceptance": float(smp.acceptance_fraction.mean())}
         del smp
+    if C > 1 and "windowed" in modes:
+        # independent candidates need no lock step: two groups of candidates, each its own staged batch, sampler and
+        # CUDA stream, stepped from two host threads (namaste_b200.CandidateBatchSampler; same chains as one batch)
+        out["windowed_one_batch"] = out["windowed"]
+        grp = nb.CandidateBatchSampler(wl["curves"], wl["priors"], W, oversamp=wl["S"], seed=1 + b.rank, groups=2)
+        grp.run_mcmc(wl["pos"], n_mcmc)
+        grp.reset()
+        b.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        grp.run_mcmc(None, n_mcmc)
+        dt = b.max_over_ranks(time.perf_counter() - t0)
+        out["windowed"] = {"steps_per_s": n_mcmc / dt, "candidate_steps_per_s": n_mcmc * C * b.world / dt,
+                           "wt_per_s": n_mcmc * C * W * N * b.world / dt, "acceptance": float(grp.acceptance_fraction.mean()),
+                           "groups": 2}
+        grp.close()
     out["steps"] = n_mcmc
     out["note"] = "one step = every walker of every candidate proposed once (two half-ensemble phases); chain kept in HBM"
     return out

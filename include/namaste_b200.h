@@ -152,6 +152,11 @@ int nmb_sampler_run_split(nmb_sampler* s, int64_t nsteps, int store_all);
 int nmb_sampler_pack_half(nmb_sampler* s, int half, int64_t k0, int64_t nk, double* out /*[nk][ndim+1]*/);
 int nmb_sampler_unpack_half(nmb_sampler* s, int half, const double* in /*[W/2][ndim+1]*/);
 int nmb_sampler_reset(nmb_sampler* s);
+/* The random stream is keyed by (seed; step, half, candidate, walker).  A catalogue of candidates stepped as several
+ * batches (one sampler and CUDA stream each -- independent candidates need no lock step, and two such groups keep the
+ * GPU busier than one) draws the numbers it would draw as ONE batch when every sampler is told the index of its
+ * first candidate.  Call before the first step.  (Reference: one Star.RunMCMC per candidate, namaste.py:526-612.) */
+int nmb_sampler_set_candidate_offset(nmb_sampler* s, int64_t cand0);
 int64_t nmb_sampler_len(const nmb_sampler* s);   /* stored chain columns */
 int64_t nmb_sampler_steps(const nmb_sampler* s); /* steps taken (RNG counter) */
 /* what: 0 pos, 1 lnp, 2 chain [ncand][W][len][6], 3 lnprobability [ncand][W][len], 4 naccepted (int64) */

@@ -10,6 +10,7 @@ from .namaste import (MonotransitModel, MonoLnPrior, MonoOnlyLogProb, MonoOnlyNe
                       stage_lightcurve, clear_cache, calcminp, calcmaxvel, monoPriors, initLD, BuildMeanPriors,
                       transit_window_mask, nonan, AnomCutDiff, initial_walkers, trim_samples, RunMCMC, Optimize_mono, VelToOrbit, PlanetRtoM, MonoFinalPars)
 from .sampler import EnsembleSampler
+from .distributed import CandidateBatchSampler
 from .gp import GP, RealTerm, JitterTerm, RotationTerm, MonoLogProb, MonoNegLogProb
 from .core import LightCurve, occultquad, lnprior, prior_table, measure_fp64_peak, launch_count, PARAM_NAMES
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "nmb_sampler_pack_half": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp]),
     "nmb_sampler_unpack_half": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "nmb_sampler_reset": (ctypes.c_int, [_vp]),
+    "nmb_sampler_set_candidate_offset": (ctypes.c_int, [_vp, ctypes.c_int64]),
     "nmb_sampler_len": (ctypes.c_int64, [_vp]),
     "nmb_sampler_steps": (ctypes.c_int64, [_vp]),
     "nmb_sampler_get": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),

@@ -716,6 +716,7 @@ struct nmb_sampler {
     int split_rank = 0, split_world = 1;
     void* peer_base[nmb::kMaxPeers] = {};
     long long split_epoch = 0;
+    int cand0 = 0;             // index of the batch's first candidate in the random stream (nmb_sampler_set_candidate_offset)
 };
 
 namespace {
@@ -755,7 +756,7 @@ int sampler_reserve(nmb_sampler* s, int64_t need) {
 
 nmb::SampleCtx sampler_ctx(nmb_sampler* s, int half, int k0, int store) {
     nmb::SampleCtx sc{};
-    sc.enabled = 1; sc.W = (int)s->W; sc.half = half; sc.k0 = k0; sc.store = store; sc.ndim = s->ndim;
+    sc.enabled = 1; sc.W = (int)s->W; sc.half = half; sc.k0 = k0; sc.c0 = s->cand0; sc.store = store; sc.ndim = s->ndim;
     sc.step = s->step; sc.tcol = s->tlen; sc.tcap = s->tcap; sc.seed = s->seed; sc.a = s->a;
     sc.pos = s->d_pos; sc.lnp = s->d_lnp; sc.q = s->d_q; sc.zz = s->d_zz; sc.logu = s->d_logu;
     sc.chain = s->d_chain; sc.lnpchain = s->d_lnpchain; sc.nacc = s->d_nacc; sc.nan_count = s->d_nan;
@@ -1073,6 +1074,13 @@ extern "C" int nmb_sampler_unpack_half(nmb_sampler* s, int half, const double* i
 extern "C" int nmb_sampler_sync(nmb_sampler* s) {
     if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_sync: null pointer");
     return sampler_check_nan(s, "lnprob returned NaN.");
+}
+
+extern "C" int nmb_sampler_set_candidate_offset(nmb_sampler* s, int64_t cand0) {
+    if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_set_candidate_offset: null pointer");
+    if (cand0 < 0 || cand0 + s->C > (1LL << 30)) return fail(NMB_ERR_ARG, "nmb_sampler_set_candidate_offset: offset out of range");
+    s->cand0 = (int)cand0;
+    return NMB_OK;
 }
 
 extern "C" int64_t nmb_sampler_len(const nmb_sampler* s) { return s ? s->tlen : -1; }

@@ -20,6 +20,8 @@ struct SampleCtx {
     int W;                // walkers per candidate (full ensemble)
     int half;             // 0: update first half, 1: update second half
     int k0;               // first walker (index within the half) evaluated by this launch
+    int c0;               // index of this batch's first candidate in the random stream (candidate groups of one
+                          // catalogue on separate samplers draw the numbers they would draw in one batch)
     int store;            // append to the chain at column tcol
     int ndim;
     long long step;       // global step counter (RNG)
@@ -78,7 +80,7 @@ __device__ __forceinline__ Draw propose_draw(const SampleCtx& sc, int cand, int 
     const int i = (sc.half == 0 ? 0 : halfk) + sc.k0 + k;  // walker being updated
     const int c_base = sc.half == 0 ? halfk : 0;           // complementary half
     uint32_t r[4], r2[4];
-    const uint32_t walker = (uint32_t)i, cnd = (uint32_t)cand;
+    const uint32_t walker = (uint32_t)i, cnd = (uint32_t)(cand + sc.c0);
     philox4x32_10((uint32_t)sc.step, (uint32_t)(sc.step >> 32), (walker << 1) | (uint32_t)sc.half, cnd << 1,
                   (uint32_t)sc.seed, (uint32_t)(sc.seed >> 32), r);
     philox4x32_10((uint32_t)sc.step, (uint32_t)(sc.step >> 32), (walker << 1) | (uint32_t)sc.half, (cnd << 1) | 1u,

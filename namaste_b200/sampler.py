@@ -74,6 +74,7 @@ class EnsembleSampler(object):
         self._have_state = False
         self.iterations = 0
         self._last = None
+        self._cand0 = 0   # index of the batch's first candidate in the random stream (CandidateBatchSampler)
 
     # ---- handle management --------------------------------------------------------------------
     def _ensure(self, rstate0):
@@ -94,6 +95,8 @@ class EnsembleSampler(object):
             check(lib.nmb_sampler_create(self._lc._h, self.k, ptr(tab), seed, self.a, MODES[self._mode],
                                          ctypes.byref(h)), "EnsembleSampler")
         self._h = h
+        if self._cand0:
+            check(lib.nmb_sampler_set_candidate_offset(h, int(self._cand0)), "EnsembleSampler")
 
     def __del__(self):
         try:

@@ -190,3 +190,34 @@ def test_split_api_refuses_bad_arguments(nb):
         SplitEnsembleSampler(staged, pri, 24, seed=1, transport="carrier pigeon")
     with pytest.raises(ValueError):
         SplitEnsembleSampler(nb.LightCurve([lc, lc]), pri, 24, seed=1)              # one light curve only
+
+
+@pytest.mark.parametrize("groups", [1, 2, 3])
+def test_candidate_groups_give_the_one_batch_chains(nb, groups):
+    """CandidateBatchSampler steps a catalogue of independent candidates as several groups (own staged batch,
+    sampler, stream and host thread each); with every group told the index of its first candidate the chains are
+    those of ONE batch under one sampler with the same seed, bit for bit."""
+    g = load_golden("synth_k2_s11")
+    base = g["lc"]
+    mid = len(base) // 2
+    cuts = [(mid - 600, mid + 500), (mid - 300, mid + 300), (0, len(base)), (mid - 900, mid + 200), (mid - 250, mid + 700)]
+    curves = [np.ascontiguousarray(base[a:b]) for a, b in cuts]
+    C, W, nsteps, seed = len(curves), 16, 6, 4242
+    rng = np.random.default_rng(8)
+    pos0 = g["walkers"][0][None, None, :] * (1 + 1e-4 * rng.standard_normal((C, W, 6)))
+    tabs = np.stack([g["priors"]] * C)
+    one_lc = nb.LightCurve(curves, oversamp=int(g["oversamp"]))
+    one = nb.EnsembleSampler(W, 6, nb.MonoOnlyLogProb, args=(one_lc, tabs), seed=seed)
+    one.run_mcmc(pos0, nsteps)
+    grp = nb.CandidateBatchSampler(curves, tabs, W, oversamp=int(g["oversamp"]), seed=seed, groups=groups)
+    pos, lnp = grp.run_mcmc(pos0, nsteps)
+    assert grp.chain.shape == (C, W, nsteps, 6)
+    assert np.array_equal(grp.chain, one.chain) and np.array_equal(grp.lnprobability, one.lnprobability)
+    assert np.array_equal(grp.naccepted, one.naccepted)
+    assert np.array_equal(pos, one.chain[:, :, -1, :]) and np.array_equal(lnp, one.lnprobability[:, :, -1])
+    pos2, _ = grp.run_mcmc(None, 2)                       # continues
+    one.run_mcmc(None, 2)
+    assert np.array_equal(pos2, one.chain[:, :, -1, :])
+    with pytest.raises(ValueError):
+        grp.run_mcmc(pos0[:2], 1)
+    grp.close()
