@@ -152,6 +152,12 @@ int nmb_sampler_run_split(nmb_sampler* s, int64_t nsteps, int store_all);
 int nmb_sampler_pack_half(nmb_sampler* s, int half, int64_t k0, int64_t nk, double* out /*[nk][ndim+1]*/);
 int nmb_sampler_unpack_half(nmb_sampler* s, int half, const double* in /*[W/2][ndim+1]*/);
 int nmb_sampler_reset(nmb_sampler* s);
+/* The current CUDA device belongs to the calling host thread (cudaGetDevice / cudaSetDevice): a thread that drives
+ * a handle created by another thread selects that thread's device first.  Every entry point that takes a light-curve
+ * handle refuses to run on another device than the one the handle was staged on. */
+int nmb_get_device(int* device);
+int nmb_set_device(int device);
+
 /* The random stream is keyed by (seed; step, half, candidate, walker).  A catalogue of candidates stepped as several
  * batches (one sampler and CUDA stream each -- independent candidates need no lock step, and two such groups keep the
  * GPU busier than one) draws the numbers it would draw as ONE batch when every sampler is told the index of its

@@ -58,6 +58,8 @@ SIGNATURES = {
     "nmb_sampler_unpack_half": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "nmb_sampler_reset": (ctypes.c_int, [_vp]),
     "nmb_sampler_set_candidate_offset": (ctypes.c_int, [_vp, ctypes.c_int64]),
+    "nmb_get_device": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "nmb_set_device": (ctypes.c_int, [ctypes.c_int]),
     "nmb_sampler_len": (ctypes.c_int64, [_vp]),
     "nmb_sampler_steps": (ctypes.c_int64, [_vp]),
     "nmb_sampler_get": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),

@@ -1076,6 +1076,18 @@ extern "C" int nmb_sampler_sync(nmb_sampler* s) {
     return sampler_check_nan(s, "lnprob returned NaN.");
 }
 
+// The current CUDA device is a property of the host THREAD: a thread that drives a handle staged by another thread
+// selects that thread's device first (CandidateBatchSampler's group threads).
+extern "C" int nmb_get_device(int* device) {
+    if (!device) return fail(NMB_ERR_ARG, "nmb_get_device: null pointer");
+    CU(cudaGetDevice(device));
+    return NMB_OK;
+}
+extern "C" int nmb_set_device(int device) {
+    CU(cudaSetDevice(device));
+    return NMB_OK;
+}
+
 extern "C" int nmb_sampler_set_candidate_offset(nmb_sampler* s, int64_t cand0) {
     if (!s) return fail(NMB_ERR_ARG, "nmb_sampler_set_candidate_offset: null pointer");
     if (cand0 < 0 || cand0 + s->C > (1LL << 30)) return fail(NMB_ERR_ARG, "nmb_sampler_set_candidate_offset: offset out of range");

@@ -232,6 +232,9 @@ class CandidateBatchSampler(object):
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
         self.ncand, self.k, self.dim = C, int(nwalkers), 6
+        dev = ctypes.c_int(0)
+        check(load().nmb_get_device(ctypes.byref(dev)), "CandidateBatchSampler")
+        self._device = int(dev.value)   # the group threads select it: the current CUDA device is per host thread
         bounds = [(C * g) // groups for g in range(groups + 1)]
         self._slices = [slice(bounds[g], bounds[g + 1]) for g in range(groups)]
         self._lcs, self._samplers = [], []
@@ -250,6 +253,7 @@ class CandidateBatchSampler(object):
 
         def work(g):
             try:
+                check(load().nmb_set_device(self._device), "CandidateBatchSampler")
                 out[g] = fn(g, self._samplers[g])
             except BaseException as e:  # noqa: BLE001 -- re-raised below
                 errs.append(e)

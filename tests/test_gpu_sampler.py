@@ -221,3 +221,23 @@ def test_candidate_groups_give_the_one_batch_chains(nb, groups):
     with pytest.raises(ValueError):
         grp.run_mcmc(pos0[:2], 1)
     grp.close()
+
+
+def test_candidate_groups_on_a_second_device(nb):
+    """The group threads select the device the sampler was created on (the current CUDA device is per host thread)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = load_golden("synth_k2_s11")
+    curves = [np.ascontiguousarray(g["lc"][a:a + 900]) for a in (1500, 1600, 1700, 1400)]
+    W, seed = 16, 99
+    pos0 = g["walkers"][0][None, None, :] * (1 + 1e-4 * np.random.default_rng(2).standard_normal((4, W, 6)))
+    tabs = np.stack([g["priors"]] * 4)
+    chains = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            grp = nb.CandidateBatchSampler(curves, tabs, W, oversamp=int(g["oversamp"]), seed=seed, groups=2)
+            grp.run_mcmc(pos0, 4)
+            chains.append(grp.chain)
+            grp.close()
+    assert np.array_equal(chains[0], chains[1])
