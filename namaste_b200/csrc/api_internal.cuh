@@ -237,10 +237,6 @@ inline int ensure_ws(nmb_lc* lc, size_t CW, size_t ntiles, cudaStream_t st) {
     return NMB_OK;
 }
 
-// blocks per SM of the next eval_slots launch (0: one resident wave).  Behind window_direct_kernel the queue only
-// holds the few long-range walkers, often nothing: a small grid is cheaper to start and to drain.
-inline thread_local int g_eval_blocks_per_sm = 0;
-
 template <int S, int MINB, int PATH>
 int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors, double* lnprob, double* loglike,
                    cudaStream_t st, const nmb::SampleCtx& sc) {
@@ -255,8 +251,7 @@ int launch_eval_mb(nmb_lc* lc, const double* params, int W, const double* priors
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEvalThreads, smem));
         per_sm = std::max(per_sm, 1);
     }
-    const int bps = g_eval_blocks_per_sm > 0 ? std::min(g_eval_blocks_per_sm, per_sm) : per_sm;
-    const int grid = sms * bps;  // one resident wave, or a part of it
+    const int grid = sms * per_sm;  // one resident wave
     CU(launch_pdl(kern, dim3(grid), dim3(kEvalThreads), smem, st, lc->view(), params, W, priors, lc->ws, sms, lnprob,
                   loglike, sc));
     g_launches++;
