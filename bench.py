@@ -165,13 +165,13 @@ def algorithmic_flops(wl):
 
 
 # FP64 instructions the kernels actually issue (per lane), counted on the ncu source pages of round 1
-# (DESIGN.md section 4): the sweep issues 1 DFMA per fine sample and one DADD per timestamp; the relaxed
+# (DESIGN.md section 4): the sweep issues 1 DFMA per fine sample and one DADD per 16-timestamp trip; the relaxed
 # stage 2 issues about 210 FP64 instructions per in-transit fine sample plus ~40 per in-transit timestamp
 # (bin mean, residual, term) -- an estimate for stage 2, exact for the sweep.
 def executed_fp64(wl, counts):
     m, m_int, m_edge, t_in = counts
     wn = wl["C"] * wl["W"] * wl["N"]
-    return m + wn, 210 * (m_int + m_edge) + 40 * t_in
+    return m + wn // 16, 210 * (m_int + m_edge) + 40 * t_in
 
 
 # --------------------------------------------------------------------------------------------
@@ -585,7 +585,7 @@ def roofline_of(b, wl, res, peak_tf, traffic):
             "peak_source": "DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 entry)",
             "flops_convention": "frac: SURVEY.md 8(d) -- 7/fine sample + 143 interior + 180 ingress + 5/timestamp + 40/walker; "
                                 "frac_executed: FP64 instructions issued per lane x 2 flops (sweep: 1 DFMA per fine sample + "
-                                "1 DADD per timestamp, exact; stage 2: ~210 per in-transit sample, from the ncu source pages)",
+                                "1 DADD per 16 timestamps, exact; stage 2: ~210 per in-transit sample, from the ncu source pages)",
             "fine_samples": m, "interior": m_int, "edge": m_edge, "in_transit_timestamps": t_in,
             "kernels": kernels,
             "whole_step": {"flops": flops, "ms": res["brute"]["ms_per_step"], "achieved": flops / step_s / 1e12,

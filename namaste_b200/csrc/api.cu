@@ -21,7 +21,7 @@ extern "C" void nmb_lc_destroy(nmb_lc* lc) {
         std::lock_guard<std::mutex> g(g_live_mu);
         g_live_lc.erase(lc);
     }
-    cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_term); cudaFree(lc->d_var); cudaFree(lc->d_modelbuf); cudaFree(lc->d_meanpar); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
+    cudaFree(lc->d_t); cudaFree(lc->d_f); cudaFree(lc->d_w); cudaFree(lc->d_term); cudaFree(lc->d_tsum); cudaFree(lc->d_var); cudaFree(lc->d_modelbuf); cudaFree(lc->d_meanpar); cudaFree(lc->d_pre_hi); cudaFree(lc->d_pre_lo);
     cudaFree(lc->d_tgrid); cudaFree(lc->d_gcount); cudaFree(lc->d_t0); cudaFree(lc->d_ginv);
     cudaFree(lc->d_off); cudaFree(lc->d_n); cudaFree(lc->d_partials); cudaFree(lc->d_tickets); cudaFree(lc->d_stage);
     cudaFree(lc->ws.partials); cudaFree(lc->ws.oot); cudaFree(lc->ws.wcs); cudaFree(lc->ws.swc); cudaFree(lc->ws.rlo); cudaFree(lc->ws.rhi);
@@ -155,6 +155,14 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
     lc->cad = cads;
     cudaGetDevice(&lc->device);
     std::vector<long long> hn(n, n + ncand);
+    // the terms of each trip of the brute-force sweep (kSweepTrip consecutive timestamps), added in timestamp order
+    std::vector<double> htsum(ncand * (npad / nmb::kSweepTrip), 0.0);
+    for (int64_t c = 0; c < ncand; ++c)
+        for (int64_t k = 0; k < npad / nmb::kSweepTrip; ++k) {
+            double acc = 0.0;
+            for (int j = 0; j < nmb::kSweepTrip; ++j) acc += hterm[c * npad + k * nmb::kSweepTrip + j];
+            htsum[c * (npad / nmb::kSweepTrip) + k] = acc;
+        }
     auto up = [&](double** dst, const std::vector<double>& src) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, src.size() * sizeof(double));
         if (e != cudaSuccess) return e;
@@ -162,7 +170,7 @@ extern "C" int nmb_lc_create_batch(const double* t, const double* flux, const do
     };
     cudaError_t e = cudaSuccess;
     if ((e = up(&lc->d_t, ht)) != cudaSuccess || (e = up(&lc->d_f, hf)) != cudaSuccess ||
-        (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_term, hterm)) != cudaSuccess || (e = up(&lc->d_var, hvar)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
+        (e = up(&lc->d_w, hw)) != cudaSuccess || (e = up(&lc->d_term, hterm)) != cudaSuccess || (e = up(&lc->d_tsum, htsum)) != cudaSuccess || (e = up(&lc->d_var, hvar)) != cudaSuccess || (e = up(&lc->d_pre_hi, hph)) != cudaSuccess ||
         (e = up(&lc->d_pre_lo, hpl)) != cudaSuccess || (e = up(&lc->d_off, hoff)) != cudaSuccess ||
         (e = up(&lc->d_t0, ht0)) != cudaSuccess || (e = up(&lc->d_ginv, hginv)) != cudaSuccess ||
         (e = cudaMalloc(&lc->d_tgrid, hgrid.size() * sizeof(int))) != cudaSuccess ||

@@ -44,13 +44,14 @@ constexpr int kSweepChunk = 64;  // timestamps per TMA chunk of the walker-per-t
 #define NMB_EVAL_MINB 5          // resident stage-2 blocks per SM of the default arithmetic (96 registers)
 #endif
 #ifndef NMB_SWEEP_MINB
-#define NMB_SWEEP_MINB 5         // resident 128-walker sweep blocks per SM (96 registers, sixteen timestamps per trip).
-                                 // With one DFMA per fine sample (profiles/r02e2_ab_sweep_minb_trip.txt), the 65 k x 4096
-                                 // sweep (S = 15) / the 500 k x 2048 one (S = 10) / the 256-candidate batch (S = 11):
-                                 // 8 per trip at 6 blocks 0.442 / 1.190 / 0.167 ms, at 5 blocks 0.468 / 1.227 / 0.158,
-                                 // 16 per trip at 5 blocks 0.438 / 1.063 / 0.165, 4 per trip at 6 blocks 0.495 / 1.273 / 0.162.
-                                 // (ptxas schedules the S = 10 loop of the 8-per-trip build with its shared-memory loads
-                                 // issued just in time; sixteen per trip at 96 registers is the stable choice.)
+#define NMB_SWEEP_MINB 4         // resident 128-walker sweep blocks per SM (124-126 registers, sixteen timestamps per trip).
+                                 // With one DFMA per fine sample and the trips' terms summed at staging time, the
+                                 // 65 k x 4096 sweep (S = 15) / the 500 k x 2048 one (S = 10) / the 256-candidate batch
+                                 // (S = 11) take 0.379 / 0.990 / 0.156 ms at 4 blocks per SM, 0.418 / 1.153 / 0.158 at 5,
+                                 // 0.428 / 1.072 / 0.160 at 6 and 0.396 / 0.945 / 0.169 at 3
+                                 // (profiles/r02z3_ab_sweep_tripsums_minb.txt): four warps per sub-partition are enough to
+                                 // keep the issue port busy (tools/micro/sweep_mix.cu) and with 128 registers ptxas
+                                 // keeps the shared-memory loads and the logic off the DFMA stream's back.
 #endif
 
 // Per-stage device timing (nmb_stage_timing / nmb_stage_times): CUDA events around stage 1 and
@@ -100,7 +101,7 @@ struct nmb_lc {
     int device = 0;
     std::vector<int64_t> n;
     std::vector<double> cad;
-    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_term = nullptr, *d_var = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
+    double *d_t = nullptr, *d_f = nullptr, *d_w = nullptr, *d_term = nullptr, *d_tsum = nullptr, *d_var = nullptr, *d_pre_hi = nullptr, *d_pre_lo = nullptr, *d_off = nullptr;
     long long* d_n = nullptr;
     int *d_tgrid = nullptr, *d_gcount = nullptr;
     double *d_t0 = nullptr, *d_ginv = nullptr;
@@ -154,7 +155,7 @@ struct nmb_lc {
 
     nmb::LcView view() const {
         nmb::LcView v;
-        v.t = d_t; v.f = d_f; v.w = d_w; v.term = d_term; v.gran = gran; v.ngran = ngran; v.pre_hi = d_pre_hi; v.pre_lo = d_pre_lo; v.off = d_off;
+        v.t = d_t; v.f = d_f; v.w = d_w; v.term = d_term; v.tsum = d_tsum; v.gran = gran; v.ngran = ngran; v.pre_hi = d_pre_hi; v.pre_lo = d_pre_lo; v.off = d_off;
         v.n = d_n; v.npad = npad; v.ncand = (int)ncand; v.S = S;
         v.tgrid = d_tgrid; v.t0 = d_t0; v.ginv = d_ginv; v.gcount = d_gcount; v.gstride = gstride;
         return v;

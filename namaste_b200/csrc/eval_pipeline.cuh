@@ -190,6 +190,7 @@ struct WalkSmem {
     double ftab[2][S > 0 ? 2 : CH * SP];  // fine-time table: run-time-S instantiation only
     double traw[2][CH];
     double term[2][CH];
+    double tsum[2][CH / kSweepTrip];  // the terms of each trip, summed in timestamp order when the light curve was staged
     double off[kMaxS];
     unsigned long long mbar[2];
     int s_scan[40];
@@ -208,11 +209,6 @@ __device__ __forceinline__ unsigned sweep_yand(double vs, double ti, const doubl
     for (int k = 0; k + 1 < S - ((S & 1) ? 0 : 2); k += 2) a &= h[k] & h[k + 1];
     return a;
 }
-#ifndef NMB_SWEEP_TRIP
-#define NMB_SWEEP_TRIP 16
-#endif
-constexpr int kSweepTrip = NMB_SWEEP_TRIP;  // timestamps per trip of the sweep's inner loop (even, divides the chunk)
-
 // One thread per walker: proposal (sampler), model constants and the sweep's classification constants, once, for
 // ensembles whose walker groups are swept by many time blocks (launched in front of sweep_walkers_kernel).
 static __global__ void __launch_bounds__(128)
@@ -280,15 +276,17 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
     const long long cw = (long long)cand * W + w;
     const double* __restrict__ gt = lc.t + (long long)cand * lc.npad;
     const double* __restrict__ gterm = lc.term + (long long)cand * lc.npad;
+    const double* __restrict__ gtsum = lc.tsum + (long long)cand * (lc.npad / kSweepTrip);
 
     if (tid == 0) {
         trace_min(ws, 0);
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
         if (c_begin < c_end) {
-            mbar_expect_tx(&sm.mbar[0], 2u * CH * sizeof(double));
+            mbar_expect_tx(&sm.mbar[0], (2u * CH + CH / kSweepTrip) * sizeof(double));
             tma_bulk_g2s(sm.traw[0], gt + (long long)c_begin * CH, CH * sizeof(double), &sm.mbar[0]);
             tma_bulk_g2s(sm.term[0], gterm + (long long)c_begin * CH, CH * sizeof(double), &sm.mbar[0]);
+            tma_bulk_g2s(sm.tsum[0], gtsum + (long long)c_begin * (CH / kSweepTrip), (CH / kSweepTrip) * sizeof(double), &sm.mbar[0]);
         }
     }
     if (tid < Sx) sm.off[tid] = lc.off[(long long)cand * Sx + tid];
@@ -349,9 +347,11 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
         // measured and is slower: 0.474 against 0.448 ms on the 65 k x 4096 sweep, profiles/r02a2_ab_sweep_ring.txt.)
         __syncthreads();
         if (tid == 0 && c + 1 < c_end) {
-            mbar_expect_tx(&sm.mbar[buf ^ 1], 2u * CH * sizeof(double));
+            mbar_expect_tx(&sm.mbar[buf ^ 1], (2u * CH + CH / kSweepTrip) * sizeof(double));
             tma_bulk_g2s(sm.traw[buf ^ 1], gt + (long long)(c + 1) * CH, CH * sizeof(double), &sm.mbar[buf ^ 1]);
             tma_bulk_g2s(sm.term[buf ^ 1], gterm + (long long)(c + 1) * CH, CH * sizeof(double), &sm.mbar[buf ^ 1]);
+            tma_bulk_g2s(sm.tsum[buf ^ 1], gtsum + (long long)(c + 1) * (CH / kSweepTrip), (CH / kSweepTrip) * sizeof(double),
+                         &sm.mbar[buf ^ 1]);
         }
         const double* tr = sm.traw[buf];
         const double* tm = sm.term[buf];
@@ -385,17 +385,21 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
                 }
             }
             for (int o = 1; o < F; o <<= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
-            if (sub == 0) {
-                if (mask == 0ull) {
-#pragma unroll 8
-                    for (int i = 0; i < CH; ++i) acc += tm[i];
-                } else {
-                    for (int i = 0; i < CH; ++i) {
-                        if ((mask >> i) & 1ull) {
-                            lo = min(lo, base + i);
-                            hi = base + i + 1;
-                        } else {
-                            acc += tm[i];
+            if (sub == 0) {   // the same association as the one-lane layout: trip sums, single terms inside marked trips
+                const double* ts = sm.tsum[buf];
+                for (int tr_ = 0; tr_ < CH / NT; ++tr_) {
+                    const unsigned long long mt = (mask >> (tr_ * NT)) & ((1ull << NT) - 1ull);
+                    if (mt == 0ull) {
+                        acc += ts[tr_];
+                    } else {
+                        for (int j = 0; j < NT; ++j) {
+                            const int i = tr_ * NT + j;
+                            if ((mt >> j) & 1ull) {
+                                lo = min(lo, base + i);
+                                hi = base + i + 1;
+                            } else {
+                                acc += tm[i];
+                            }
                         }
                     }
                 }
@@ -403,20 +407,22 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
         } else if (S > 0) {
             // NT timestamps per trip.  The common case -- none of them can be in transit -- costs, beside the
             // S DFMA and S / 2 logic operations per timestamp, one more AND, a bit test and a branch per
-            // trip and one DADD per timestamp; the per-timestamp book-keeping runs only on the rare trips that
-            // touch the transit.  Terms are added in timestamp order on both paths.
+            // trip and ONE DADD: the trip's terms were summed (in timestamp order) when the light curve was staged.
+            // The per-timestamp book-keeping, and the terms themselves, are touched only on the rare trips that
+            // reach the transit; a walker's partial sum is therefore "trip sums, and single terms inside the trips
+            // around its transit", the same association on every launch shape and lane layout.
             constexpr int NT = kSweepTrip;
+            const double* ts = sm.tsum[buf];
 #pragma unroll 1
             for (int i0 = 0; i0 < CH; i0 += NT) {
-                double tt[NT], mm[NT];
+                double tt[NT];
                 unsigned q[NT];
 #pragma unroll
                 for (int j = 0; j < NT; j += 2) {
                     const double2 tv = *reinterpret_cast<const double2*>(tr + i0 + j);
-                    const double2 mv = *reinterpret_cast<const double2*>(tm + i0 + j);
                     tt[j] = tv.x; tt[j + 1] = tv.y;
-                    mm[j] = mv.x; mm[j + 1] = mv.y;
                 }
+                const double tsum = ts[i0 / NT];
                 unsigned qall = 0xffffffffu;
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
@@ -424,13 +430,12 @@ sweep_walkers_kernel(LcView lc, const double* __restrict__ params, int W, int gp
                     qall &= q[j];
                 }
                 if (qall & kSweepOutBit) {
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) acc += mm[j];
+                    acc += tsum;
                 } else {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
                         if (q[j] & kSweepOutBit) {
-                            acc += mm[j];
+                            acc += tm[i0 + j];
                         } else {
                             lo = min(lo, base + i0 + j);
                             hi = base + i0 + j + 1;

@@ -27,6 +27,7 @@ struct LcView {
     const double* f;       // [C][npad]
     const double* w;       // [C][npad]   -2 * err**-2            (namaste.py:1347)
     const double* term;    // [C][npad]   w * (f - 1)^2: chi^2 term of a timestamp whose model is exactly 1
+    const double* tsum;    // [C][npad/kSweepTrip]  the terms of each trip of the brute-force sweep, added in timestamp order
     const double* pre_hi;  // [C][npad+1] prefix sum of w*(f-1)^2, high word
     const double* pre_lo;  // [C][npad+1] low word (double-double)
     const double* off;     // [C][S]      cad * (k * (1/S))        (namaste.py:1159)
@@ -178,6 +179,7 @@ __device__ __forceinline__ double sample_flux(double ti, double offk, const Walk
     return occultquad_point<false>(z, wc.q, nullptr, nullptr, nullptr);
 }
 
+constexpr int kSweepTrip = 16;  // timestamps per trip of the brute-force sweep's inner loop (divides its 64-timestamp chunk)
 constexpr int kMaxS = 32;
 constexpr int kWTMax = 8;
 

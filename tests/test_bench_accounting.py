@@ -32,7 +32,7 @@ def test_flop_accounting_matches_a_direct_count():
     assert fl_eval == 143 * m_int + 180 * m_edge + 5 * t_in + 40 * wl["W"]
     assert flops == fl_sweep + fl_eval
     ex_sweep, ex_eval = bench.executed_fp64(wl, counts)
-    assert ex_sweep == m + wn          # one DFMA per fine sample + one DADD per timestamp
+    assert ex_sweep == m + wn // 16    # one DFMA per fine sample + one DADD per 16-timestamp trip
     assert ex_eval == 210 * (m_int + m_edge) + 40 * t_in
 
 
