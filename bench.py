@@ -593,7 +593,7 @@ def roofline_of(b, wl, res, peak_tf, traffic):
                            "frac_executed": 2.0 * (ex_sweep + ex_eval) / step_s / 1e12 / peak_tf},
             "note": "dominant kernel = the longer of the two launches of a brute-force step; per-kernel durations from "
                     "CUDA events between the kernels (they do not overlap while measured).  The sweep classifies a fine "
-                    "sample with ONE DFMA since profiles/r02w (two before: frac_executed 0.75 at 0.652 ms, now ~0.67 at "
+                    "sample with ONE DFMA since profiles/r02w (two before: frac_executed 0.75 at 0.652 ms, now ~0.63 at "
                     "~0.38 ms for the same work); what bounds it is the issue port of the sub-partition -- a DFMA holds it "
                     "two cycles, the S/2 LOP3 + DADD + LDS per timestamp do not issue under it (DESIGN.md section 4, "
                     "tools/micro/sweep_mix.cu)"}
